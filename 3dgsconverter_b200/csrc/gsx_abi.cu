@@ -1,0 +1,273 @@
+// gsx_abi.cu -- the extern "C" surface of libgsx.so (declared in include/gsx.h).
+//
+// Thin: argument checks, workspace carving, stream plumbing and the host-buffer convenience
+// entry points.  No torch types, no C++ types in any signature.
+#include "../../include/gsx.h"
+
+#include "gsx_common.cuh"
+#include "gsx_density.cuh"
+#include "gsx_kmeans.cuh"
+#include "gsx_masks.cuh"
+#include "gsx_sor.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace gsx {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count() {
+    static int cached_dev = -1, cached = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev != cached_dev) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        cached = v;
+        cached_dev = dev;
+    }
+    return cached;
+}
+
+struct DevBuf {  // stream-ordered device allocation for the *_host entry points
+    void* p = nullptr;
+    cudaStream_t st;
+    explicit DevBuf(cudaStream_t s) : st(s) {}
+    int alloc(size_t bytes) {
+        cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 1, st);
+        if (e != cudaSuccess) {
+            set_error("cudaMallocAsync(%zu) -> %s", bytes, cudaGetErrorString(e));
+            p = nullptr;
+            return GSX_ERR_CUDA;
+        }
+        return GSX_OK;
+    }
+    ~DevBuf() {
+        if (p) cudaFreeAsync(p, st);
+    }
+};
+
+}  // namespace gsx
+
+using namespace gsx;
+
+extern "C" {
+
+const char* gsx_last_error(void) { return g_err; }
+int gsx_version(void) { return 100; }
+int gsx_device_sm_count(void) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return GSX_ERR_CUDA;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return GSX_ERR_CUDA;
+    return v;
+}
+
+/* ------------------------------------------------------------------ SOR */
+
+int64_t gsx_sor_workspace_bytes(int64_t n) { return sor_workspace_bytes(n); }
+
+static int carve_checked(void* ws, int64_t ws_bytes, int64_t n, SorWs& w) {
+    GSX_REQUIRE(n >= 1 && n < 2147483584ll, GSX_ERR_ARG, "sor: n=%lld out of range [1, 2^31-64)", (long long)n);
+    GSX_REQUIRE(ws != nullptr, GSX_ERR_WORKSPACE, "sor: null workspace");
+    w = sor_carve(ws, ws_bytes, n, sor_cub_bytes(n));
+    GSX_REQUIRE(w.ok, GSX_ERR_WORKSPACE, "sor: workspace too small (%lld < %zu)", (long long)ws_bytes, w.total);
+    return GSX_OK;
+}
+
+int gsx_sor_minmax(const float* xyz_dev, int64_t n, float* minmax_dev, void* ws, int64_t ws_bytes, void* stream) {
+    SorWs w;
+    int rc = carve_checked(ws, ws_bytes, n, w);
+    if (rc) return rc;
+    return sor_minmax(xyz_dev, n, minmax_dev, w.partial, (cudaStream_t)stream);
+}
+
+/* gpu_ops.py:203-213 with NumPy-2 semantics: extent/vol in float32; vol<=0 -> python float 1.0 (then
+ * float64 arithmetic); avg = max(1e-8, vol/N) keeps the float32 unless the python float wins; the
+ * cube root is float32 powf for a float32 base, float64 pow otherwise; floor of 1e-4. */
+float gsx_sor_cell_size(const float* mm, int64_t n) {
+    float ex = mm[3] - mm[0], ey = mm[4] - mm[1], ez = mm[5] - mm[2];
+    float vol = (ex * ey) * ez;
+    double cell;
+    if (vol <= 0.0f || vol != vol) {
+        if (vol != vol) {
+            cell = NAN;
+        } else {
+            double avg = 1.0 / (double)n;
+            if (!(avg > 1e-8)) avg = 1e-8;
+            cell = pow(avg * 32.0, 1.0 / 3.0);
+        }
+    } else {
+        float avgf = vol / (float)n;
+        if ((double)avgf > 1e-8) {  /* python max(1e-8, avgf) returns avgf only if avgf > 1e-8 */
+            float cv = avgf * 32.0f;
+            cell = (double)powf(cv, (float)(1.0 / 3.0));
+        } else {
+            cell = pow(1e-8 * 32.0, 1.0 / 3.0);
+        }
+    }
+    if (!(cell > 1e-4)) cell = 1e-4; /* max(cell_size, 1e-4) */
+    return (float)cell;
+}
+
+int gsx_sor_build(const float* xyz_dev, int64_t n, const float* bmin_host, float cell, void* ws, int64_t ws_bytes,
+                  void* stream) {
+    SorWs w;
+    int rc = carve_checked(ws, ws_bytes, n, w);
+    if (rc) return rc;
+    GSX_REQUIRE(cell > 0.f, GSX_ERR_ARG, "sor: cell size must be > 0");
+    return sor_build(xyz_dev, n, bmin_host, cell, w, (cudaStream_t)stream);
+}
+
+int gsx_sor_mean_dists_range(int64_t n, int64_t q_begin, int64_t q_end, int32_t k, int32_t hash_mode,
+                             const float* bmin_host, float cell, void* ws, int64_t ws_bytes, float* final_means_dev,
+                             unsigned long long* stats_dev, void* stream) {
+    SorWs w;
+    int rc = carve_checked(ws, ws_bytes, n, w);
+    if (rc) return rc;
+    return sor_mean_dists(w, q_begin, q_end, k, hash_mode, bmin_host, cell, final_means_dev, stats_dev,
+                          (cudaStream_t)stream);
+}
+
+int gsx_sor_mean_dists(int64_t n, int32_t k, int32_t hash_mode, const float* bmin_host, float cell, void* ws,
+                       int64_t ws_bytes, float* final_means_dev, unsigned long long* stats_dev, void* stream) {
+    return gsx_sor_mean_dists_range(n, 0, n, k, hash_mode, bmin_host, cell, ws, ws_bytes, final_means_dev, stats_dev,
+                                    stream);
+}
+
+int64_t gsx_mean_std_workspace_bytes(int64_t n) { return (int64_t)mean_std_ws_bytes(n); }
+
+int gsx_mean_std_f32(const float* a_dev, int64_t n, float* out_dev, void* ws, int64_t ws_bytes, void* stream) {
+    return mean_std_f32(a_dev, n, out_dev, ws, (size_t)ws_bytes, (cudaStream_t)stream);
+}
+
+int gsx_threshold_mask(const float* a_dev, int64_t n, const float* meanstd_dev, float threshold_factor,
+                       uint8_t* mask_dev, void* stream) {
+    return threshold_mask(a_dev, n, meanstd_dev, threshold_factor, mask_dev, (cudaStream_t)stream);
+}
+
+int gsx_sor_filter_device(const float* xyz_dev, int64_t n, int32_t k, float threshold_factor, int32_t hash_mode,
+                          uint8_t* mask_dev, float* means_dev, void* ws, int64_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    SorWs w;
+    int rc = carve_checked(ws, ws_bytes, n, w);
+    if (rc) return rc;
+    GSX_REQUIRE(k >= 1, GSX_ERR_ARG, "sor: k must be >= 1 (got %d)", k);
+    if ((rc = sor_minmax(xyz_dev, n, w.minmax, w.partial, st))) return rc;
+    float mm[6];
+    GSX_CUDA_CHECK(cudaMemcpyAsync(mm, w.minmax, sizeof(mm), cudaMemcpyDeviceToHost, st));
+    GSX_CUDA_CHECK(cudaStreamSynchronize(st));
+    float cell = gsx_sor_cell_size(mm, n);
+    GSX_REQUIRE(cell == cell, GSX_ERR_ARG, "sor: non-finite coordinates");
+    if ((rc = sor_build(xyz_dev, n, mm, cell, w, st))) return rc;
+    // the keys buffers are dead after the build: park the means there when the caller wants none
+    float* means = means_dev ? means_dev : reinterpret_cast<float*>(w.keys0);
+    if ((rc = sor_mean_dists(w, 0, n, k, hash_mode, mm, cell, means, nullptr, st))) return rc;
+    if ((rc = mean_std_f32(means, n, w.meanstd, w.ms_ws, w.ms_bytes, st))) return rc;
+    return threshold_mask(means, n, w.meanstd, threshold_factor, mask_dev, st);
+}
+
+int gsx_sor_filter_host(const float* xyz_host, int64_t n, int32_t k, float threshold_factor, int32_t hash_mode,
+                        uint8_t* mask_host, float* means_host) {
+    GSX_REQUIRE(n >= 1 && n < 2147483584ll, GSX_ERR_ARG, "sor: n=%lld out of range", (long long)n);
+    cudaStream_t st = 0;
+    int64_t wsb = sor_workspace_bytes(n);
+    DevBuf xyz(st), ws(st), mask(st), means(st);
+    int rc;
+    if ((rc = xyz.alloc((size_t)n * 12))) return rc;
+    if ((rc = ws.alloc((size_t)wsb))) return rc;
+    if ((rc = mask.alloc((size_t)n))) return rc;
+    if ((rc = means.alloc((size_t)n * 4))) return rc;
+    GSX_CUDA_CHECK(cudaMemcpyAsync(xyz.p, xyz_host, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+    if ((rc = gsx_sor_filter_device((const float*)xyz.p, n, k, threshold_factor, hash_mode, (uint8_t*)mask.p,
+                                    (float*)means.p, ws.p, wsb, st)))
+        return rc;
+    GSX_CUDA_CHECK(cudaMemcpyAsync(mask_host, mask.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (means_host) GSX_CUDA_CHECK(cudaMemcpyAsync(means_host, means.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    GSX_CUDA_CHECK(cudaStreamSynchronize(st));
+    return GSX_OK;
+}
+
+/* ------------------------------------------------------------------ bbox / alpha */
+
+int gsx_bbox_mask(const float* xyz_dev, int64_t n, const float* lohi_host, uint8_t* mask_dev, void* stream) {
+    GSX_REQUIRE(n >= 0, GSX_ERR_ARG, "bbox: n < 0");
+    return bbox_mask(xyz_dev, n, lohi_host, mask_dev, (cudaStream_t)stream);
+}
+
+int gsx_alpha_mask(const float* opacity_dev, int64_t n, double logit_thresh, uint8_t* mask_dev, void* stream) {
+    GSX_REQUIRE(n >= 0, GSX_ERR_ARG, "alpha: n < 0");
+    return alpha_mask(opacity_dev, n, logit_thresh, mask_dev, (cudaStream_t)stream);
+}
+
+double gsx_alpha_logit_threshold(double min_opacity_u8) {
+    double a = min_opacity_u8 / 255.0;
+    if (a < 1e-6) a = 1e-6;
+    if (a > 1.0 - 1e-6) a = 1.0 - 1e-6;
+    return log(a / (1.0 - a));
+}
+
+/* ------------------------------------------------------------------ density */
+
+int64_t gsx_density_workspace_bytes(int64_t n, int64_t cap) { return density_workspace_bytes(n, cap); }
+
+int gsx_density_voxel_count(const float* xyz_dev, int64_t n, float voxel, int64_t min_points, int64_t* dense_vox_host,
+                            int32_t* dense_cnt_host, int64_t cap, int64_t* n_dense_host, int64_t* n_voxels_host,
+                            void* ws, int64_t ws_bytes, void* stream) {
+    return density_voxel_count(xyz_dev, n, voxel, min_points, dense_vox_host, dense_cnt_host, cap, n_dense_host,
+                               n_voxels_host, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int gsx_density_member_mask(const float* xyz_dev, int64_t n, float voxel, const int64_t* keep_vox_host, int64_t n_keep,
+                            uint8_t* mask_dev, void* ws, int64_t ws_bytes, void* stream) {
+    return density_member_mask(xyz_dev, n, voxel, keep_vox_host, n_keep, mask_dev, ws, ws_bytes,
+                               (cudaStream_t)stream);
+}
+
+/* ------------------------------------------------------------------ K-Means */
+
+int64_t gsx_kmeans_workspace_bytes(int64_t n_total, int32_t nprob, int32_t K, int32_t D) {
+    return kmeans_workspace_bytes(n_total, nprob, K, D);
+}
+
+int gsx_kmeans_lloyd_device(const float* X_dev, const int64_t* row_off_host, int32_t nprob, int32_t K, int32_t D,
+                            int32_t max_iter, float* C_dev, int32_t* labels_dev, int32_t* counts_dev, void* ws,
+                            int64_t ws_bytes, void* stream) {
+    return kmeans_lloyd(X_dev, row_off_host, nprob, K, D, max_iter, C_dev, labels_dev, counts_dev, ws, ws_bytes,
+                        (cudaStream_t)stream);
+}
+
+int gsx_kmeans_host(const float* X_host, int64_t n, int32_t K, int32_t D, int32_t max_iter, float* C_host_inout,
+                    int32_t* labels_host) {
+    GSX_REQUIRE(n >= 1 && K >= 1 && D >= 1, GSX_ERR_ARG, "kmeans: bad shape");
+    cudaStream_t st = 0;
+    DevBuf X(st), C(st), L(st), cnt(st), ws(st);
+    int rc;
+    int64_t wsb = kmeans_workspace_bytes(n, 1, K, D);
+    if ((rc = X.alloc((size_t)n * D * 4))) return rc;
+    if ((rc = C.alloc((size_t)K * D * 4))) return rc;
+    if ((rc = L.alloc((size_t)n * 4))) return rc;
+    if ((rc = cnt.alloc((size_t)K * 4))) return rc;
+    if ((rc = ws.alloc((size_t)wsb))) return rc;
+    GSX_CUDA_CHECK(cudaMemcpyAsync(X.p, X_host, (size_t)n * D * 4, cudaMemcpyHostToDevice, st));
+    GSX_CUDA_CHECK(cudaMemcpyAsync(C.p, C_host_inout, (size_t)K * D * 4, cudaMemcpyHostToDevice, st));
+    GSX_CUDA_CHECK(cudaMemsetAsync(L.p, 0, (size_t)n * 4, st));
+    int64_t off[2] = {0, n};
+    if ((rc = kmeans_lloyd((const float*)X.p, off, 1, K, D, max_iter, (float*)C.p, (int*)L.p, (int*)cnt.p, ws.p, wsb, st)))
+        return rc;
+    GSX_CUDA_CHECK(cudaMemcpyAsync(C_host_inout, C.p, (size_t)K * D * 4, cudaMemcpyDeviceToHost, st));
+    GSX_CUDA_CHECK(cudaMemcpyAsync(labels_host, L.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    GSX_CUDA_CHECK(cudaStreamSynchronize(st));
+    return GSX_OK;
+}
+
+}  // extern "C"

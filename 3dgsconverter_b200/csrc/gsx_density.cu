@@ -1,0 +1,282 @@
+// gsx_density.cu -- voxel histogram and voxel-membership mask of the density filter.
+//
+// Replaces data_processor.py:38-52 (quantise, np.unique(axis=0) with counts, dense = counts >=
+// min_points) and :111-114 (per-point membership of the kept voxels).  The connected-component
+// step in between (:59-106) stays on the host: it runs over at most N/min_points dense voxels
+// and its tie-breaking depends on CPython set iteration order.
+//
+// Instead of the reference's lexicographic sort of N int64 triples, voxels are counted with
+// atomics: on a dense int32 grid over the voxel bounding box when that fits the workspace,
+// otherwise in an open-addressing hash table keyed by the packed relative voxel coordinate.
+// The thread whose increment makes a voxel reach the density threshold appends it to the
+// dense list, so no pass over the grid is needed.  q = floor(x / f32(voxel)) uses the float32
+// division of the reference (NumPy-2 weak-scalar semantics).
+#include "gsx_density.cuh"
+#include "gsx_sor.cuh"
+
+#include <math.h>
+#include <vector>
+
+namespace gsx {
+
+constexpr int kAxisBits = 21;
+constexpr long long kAxisLim = 1ll << kAxisBits;
+
+__host__ __device__ __forceinline__ long long voxel_of(float v, float voxel) {
+#ifdef __CUDA_ARCH__
+    return (long long)floorf(__fdiv_rn(v, voxel));
+#else
+    return (long long)floorf(v / voxel);
+#endif
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33;
+    return x;
+}
+static inline uint64_t mix64_host(uint64_t x) {
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33;
+    return x;
+}
+
+struct VoxGrid {
+    long long q0[3];   // voxel-space origin
+    long long dim[3];  // extent in voxels
+};
+
+int64_t density_workspace_bytes(int64_t n, int64_t cap) {
+    if (n < 1) n = 1;
+    if (cap < 1) cap = 1;
+    // hash path: table of >= 2n slots (power of two), 8-byte key + 4-byte count; plus minmax scratch
+    size_t slots = 64;
+    while (slots < (size_t)2 * n) slots <<= 1;
+    return (int64_t)(slots * 12 + 6 * 1024 * 4 + (size_t)cap * 28 + 8192);
+}
+
+// ---------------------------------------------------------------- dense-grid path
+__global__ void __launch_bounds__(256) k_vox_count_grid(const float* __restrict__ xyz, int64_t n, float voxel,
+                                                        VoxGrid g, int thr, int* __restrict__ grid,
+                                                        unsigned long long* __restrict__ counters,
+                                                        long long* __restrict__ dense_vox, int64_t cap) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long qx = voxel_of(xyz[3 * i], voxel), qy = voxel_of(xyz[3 * i + 1], voxel),
+              qz = voxel_of(xyz[3 * i + 2], voxel);
+    size_t idx = ((size_t)(qx - g.q0[0]) * g.dim[1] + (size_t)(qy - g.q0[1])) * g.dim[2] + (size_t)(qz - g.q0[2]);
+    int old = atomicAdd(grid + idx, 1);
+    if (old == 0) atomicAdd(counters + 1, 1ull);  // number of distinct voxels
+    if (old + 1 == thr) {
+        unsigned long long slot = atomicAdd(counters, 1ull);
+        if ((int64_t)slot < cap) {
+            dense_vox[3 * slot] = qx;
+            dense_vox[3 * slot + 1] = qy;
+            dense_vox[3 * slot + 2] = qz;
+        }
+    }
+}
+
+__global__ void k_vox_dense_counts_grid(const long long* __restrict__ dense_vox, int64_t nd, VoxGrid g,
+                                        const int* __restrict__ grid, int* __restrict__ dense_cnt) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nd) return;
+    size_t idx = ((size_t)(dense_vox[3 * s] - g.q0[0]) * g.dim[1] + (size_t)(dense_vox[3 * s + 1] - g.q0[1])) * g.dim[2] +
+                 (size_t)(dense_vox[3 * s + 2] - g.q0[2]);
+    dense_cnt[s] = grid[idx];
+}
+
+// ---------------------------------------------------------------- hash path
+__device__ __forceinline__ uint64_t pack_rel(long long rx, long long ry, long long rz) {
+    return (((uint64_t)rx << (2 * kAxisBits)) | ((uint64_t)ry << kAxisBits) | (uint64_t)rz) + 1ull;  // 0 = empty
+}
+
+__global__ void __launch_bounds__(256) k_vox_count_hash(const float* __restrict__ xyz, int64_t n, float voxel,
+                                                        VoxGrid g, int thr, unsigned long long* hkeys,
+                                                        int* hcnt, uint64_t slot_mask,
+                                                        unsigned long long* __restrict__ counters,
+                                                        long long* __restrict__ dense_vox, int64_t cap) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long qx = voxel_of(xyz[3 * i], voxel), qy = voxel_of(xyz[3 * i + 1], voxel),
+              qz = voxel_of(xyz[3 * i + 2], voxel);
+    uint64_t key = pack_rel(qx - g.q0[0], qy - g.q0[1], qz - g.q0[2]);
+    uint64_t s = mix64(key) & slot_mask;
+    for (;;) {
+        unsigned long long cur = hkeys[s];
+        if (cur == 0ull) {
+            unsigned long long prev = atomicCAS(hkeys + s, 0ull, (unsigned long long)key);
+            cur = prev == 0ull ? (unsigned long long)key : prev;
+        }
+        if (cur == key) break;
+        s = (s + 1) & slot_mask;
+    }
+    int old = atomicAdd(hcnt + s, 1);
+    if (old == 0) atomicAdd(counters + 1, 1ull);
+    if (old + 1 == thr) {
+        unsigned long long slot = atomicAdd(counters, 1ull);
+        if ((int64_t)slot < cap) {
+            dense_vox[3 * slot] = qx;
+            dense_vox[3 * slot + 1] = qy;
+            dense_vox[3 * slot + 2] = qz;
+        }
+    }
+}
+
+__global__ void k_vox_dense_counts_hash(const long long* __restrict__ dense_vox, int64_t nd, VoxGrid g,
+                                        const unsigned long long* __restrict__ hkeys, const int* __restrict__ hcnt,
+                                        uint64_t slot_mask, int* __restrict__ dense_cnt) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nd) return;
+    uint64_t key = pack_rel(dense_vox[3 * t] - g.q0[0], dense_vox[3 * t + 1] - g.q0[1], dense_vox[3 * t + 2] - g.q0[2]);
+    uint64_t s = mix64(key) & slot_mask;
+    while (hkeys[s] != key) s = (s + 1) & slot_mask;
+    dense_cnt[t] = hcnt[s];
+}
+
+int density_voxel_count(const float* xyz, int64_t n, float voxel, int64_t min_points, int64_t* dense_vox_host,
+                        int32_t* dense_cnt_host, int64_t cap, int64_t* n_dense_host, int64_t* n_voxels_host, void* ws,
+                        int64_t ws_bytes, cudaStream_t st) {
+    GSX_REQUIRE(n >= 1, GSX_ERR_ARG, "density: n must be >= 1");
+    GSX_REQUIRE(voxel > 0.f, GSX_ERR_ARG, "density: voxel size must be > 0");
+    GSX_REQUIRE(ws_bytes >= density_workspace_bytes(n, cap), GSX_ERR_WORKSPACE, "density: workspace too small");
+    GSX_REQUIRE(cap >= 1, GSX_ERR_ARG, "density: cap must be >= 1");
+    Carver c(ws, (size_t)ws_bytes);
+    float* partial = c.take<float>(6 * 1024);
+    float* minmax = c.take<float>(8);
+    unsigned long long* counters = c.take<unsigned long long>(4);
+    long long* dvox = c.take<long long>(3 * (size_t)cap);
+    int* dcnt = c.take<int>((size_t)cap);
+    size_t used = align_up(c.off, 256);
+    GSX_REQUIRE(c.ok() && used < (size_t)ws_bytes, GSX_ERR_WORKSPACE, "density: workspace too small for cap=%lld",
+                (long long)cap);
+    char* blob = (char*)ws + used;
+    size_t blob_bytes = (size_t)ws_bytes - used;
+
+    int rc = sor_minmax(xyz, n, minmax, partial, st);
+    if (rc) return rc;
+    float mm[6];
+    GSX_CUDA_CHECK(cudaMemcpyAsync(mm, minmax, sizeof(mm), cudaMemcpyDeviceToHost, st));
+    GSX_CUDA_CHECK(cudaStreamSynchronize(st));
+    VoxGrid g;
+    double cells = 1.0;
+    for (int a = 0; a < 3; ++a) {
+        g.q0[a] = voxel_of(mm[a], voxel);  // floor(x/voxel) is monotone in x: min/max commute with it
+        long long q1 = voxel_of(mm[3 + a], voxel);
+        g.dim[a] = q1 - g.q0[a] + 1;
+        GSX_REQUIRE(g.dim[a] >= 1 && g.dim[a] < kAxisLim, GSX_ERR_UNSUPPORTED,
+                    "density: voxel grid extent %lld on axis %d exceeds 2^21", g.dim[a], a);
+        cells *= (double)g.dim[a];
+    }
+    long long thr_ll = min_points < 1 ? 1 : min_points;
+    GSX_REQUIRE(thr_ll < 2147483647ll, GSX_ERR_ARG, "density: min_points too large");
+    int thr = (int)thr_ll;
+    GSX_CUDA_CHECK(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), st));
+    int blocks = (int)((n + 255) / 256);
+    bool use_grid = cells * 4.0 <= (double)blob_bytes;
+    uint64_t slot_mask = 0;
+    unsigned long long* hkeys = nullptr;
+    int* hcnt = nullptr;
+    if (use_grid) {
+        size_t ncell = (size_t)g.dim[0] * g.dim[1] * g.dim[2];
+        GSX_CUDA_CHECK(cudaMemsetAsync(blob, 0, ncell * 4, st));
+        k_vox_count_grid<<<blocks, 256, 0, st>>>(xyz, n, voxel, g, thr, (int*)blob, counters, dvox, cap);
+    } else {
+        size_t slots = 64;
+        while (slots < (size_t)2 * n) slots <<= 1;
+        GSX_REQUIRE(slots * 12 <= blob_bytes, GSX_ERR_WORKSPACE, "density: workspace too small for the hash table");
+        hkeys = (unsigned long long*)blob;
+        hcnt = (int*)(blob + slots * 8);
+        slot_mask = slots - 1;
+        GSX_CUDA_CHECK(cudaMemsetAsync(blob, 0, slots * 12, st));
+        k_vox_count_hash<<<blocks, 256, 0, st>>>(xyz, n, voxel, g, thr, hkeys, hcnt, slot_mask, counters, dvox, cap);
+    }
+    GSX_KERNEL_CHECK();
+    unsigned long long hc[2];
+    GSX_CUDA_CHECK(cudaMemcpyAsync(hc, counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    GSX_CUDA_CHECK(cudaStreamSynchronize(st));
+    *n_dense_host = (int64_t)hc[0];
+    if (n_voxels_host) *n_voxels_host = (int64_t)hc[1];
+    GSX_REQUIRE((int64_t)hc[0] <= cap, GSX_ERR_WORKSPACE, "density: %llu dense voxels exceed cap %lld", hc[0],
+                (long long)cap);
+    int64_t nd = (int64_t)hc[0];
+    if (nd > 0) {
+        int b2 = (int)((nd + 127) / 128);
+        if (use_grid) k_vox_dense_counts_grid<<<b2, 128, 0, st>>>(dvox, nd, g, (const int*)blob, dcnt);
+        else k_vox_dense_counts_hash<<<b2, 128, 0, st>>>(dvox, nd, g, hkeys, hcnt, slot_mask, dcnt);
+        GSX_KERNEL_CHECK();
+        GSX_CUDA_CHECK(cudaMemcpyAsync(dense_vox_host, dvox, (size_t)nd * 24, cudaMemcpyDeviceToHost, st));
+        GSX_CUDA_CHECK(cudaMemcpyAsync(dense_cnt_host, dcnt, (size_t)nd * 4, cudaMemcpyDeviceToHost, st));
+        GSX_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    return GSX_OK;
+}
+
+// ---------------------------------------------------------------- membership mask
+__global__ void __launch_bounds__(256) k_vox_member(const float* __restrict__ xyz, int64_t n, float voxel,
+                                                    long long ox, long long oy, long long oz,
+                                                    const unsigned long long* __restrict__ set, uint64_t slot_mask,
+                                                    uint8_t* __restrict__ mask) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long rx = voxel_of(xyz[3 * i], voxel) - ox, ry = voxel_of(xyz[3 * i + 1], voxel) - oy,
+              rz = voxel_of(xyz[3 * i + 2], voxel) - oz;
+    uint8_t keep = 0;
+    if (rx >= 0 && ry >= 0 && rz >= 0 && rx < kAxisLim && ry < kAxisLim && rz < kAxisLim) {
+        uint64_t key = pack_rel(rx, ry, rz);
+        uint64_t s = mix64(key) & slot_mask;
+        for (;;) {
+            unsigned long long cur = __ldg(set + s);
+            if (cur == key) {
+                keep = 1;
+                break;
+            }
+            if (cur == 0ull) break;
+            s = (s + 1) & slot_mask;
+        }
+    }
+    mask[i] = keep;
+}
+
+int density_member_mask(const float* xyz, int64_t n, float voxel, const int64_t* keep, int64_t n_keep, uint8_t* mask,
+                        void* ws, int64_t ws_bytes, cudaStream_t st) {
+    if (n == 0) return GSX_OK;
+    GSX_REQUIRE(voxel > 0.f, GSX_ERR_ARG, "density: voxel size must be > 0");
+    if (n_keep == 0) {
+        GSX_CUDA_CHECK(cudaMemsetAsync(mask, 0, (size_t)n, st));
+        return GSX_OK;
+    }
+    long long o[3] = {keep[0], keep[1], keep[2]}, hi[3] = {keep[0], keep[1], keep[2]};
+    for (int64_t t = 1; t < n_keep; ++t)
+        for (int a = 0; a < 3; ++a) {
+            if (keep[3 * t + a] < o[a]) o[a] = keep[3 * t + a];
+            if (keep[3 * t + a] > hi[a]) hi[a] = keep[3 * t + a];
+        }
+    for (int a = 0; a < 3; ++a)
+        GSX_REQUIRE(hi[a] - o[a] < kAxisLim, GSX_ERR_UNSUPPORTED, "density: kept voxels span more than 2^21 on axis %d", a);
+    size_t slots = 64;
+    while (slots < (size_t)2 * n_keep) slots <<= 1;
+    GSX_REQUIRE(slots * 8 <= (size_t)ws_bytes, GSX_ERR_WORKSPACE, "density: workspace too small for the keep set");
+    std::vector<unsigned long long> tab(slots, 0ull);
+    for (int64_t t = 0; t < n_keep; ++t) {
+        uint64_t key = ((((uint64_t)(keep[3 * t] - o[0])) << (2 * kAxisBits)) |
+                        (((uint64_t)(keep[3 * t + 1] - o[1])) << kAxisBits) | (uint64_t)(keep[3 * t + 2] - o[2])) + 1ull;
+        uint64_t s = mix64_host(key) & (slots - 1);
+        while (tab[s] != 0ull && tab[s] != key) s = (s + 1) & (slots - 1);
+        tab[s] = key;
+    }
+    GSX_CUDA_CHECK(cudaMemcpyAsync(ws, tab.data(), slots * 8, cudaMemcpyHostToDevice, st));
+    GSX_CUDA_CHECK(cudaStreamSynchronize(st));  // tab is a stack-owned pageable buffer
+    k_vox_member<<<(int)((n + 255) / 256), 256, 0, st>>>(xyz, n, voxel, o[0], o[1], o[2],
+                                                         (const unsigned long long*)ws, slots - 1, mask);
+    GSX_KERNEL_CHECK();
+    return GSX_OK;
+}
+
+}  // namespace gsx

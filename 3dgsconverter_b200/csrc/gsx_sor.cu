@@ -1,0 +1,498 @@
+// gsx_sor.cu -- Statistical Outlier Removal, Taichi semantics, for sm_100a.
+//
+// Replaces /root/reference/gsconverter/processing/gpu_ops.py:193-263 (host driver
+// filter_sor_gpu) and :98-176 (Taichi kernel sor_compute_mean_dists).  Normative
+// arithmetic: SURVEY.md Appendix A.1.
+//
+// Design (B200-first, not a translation of the Taichi kernel):
+//   * grid build entirely on device: min/max reduce -> 64-bit key (bucket hash << 18 |
+//     6+6+6-bit Morton code of the position inside the cell) -> radix sort -> float4
+//     gather (w carries the original index, so the "unsort" is fused into the query
+//     kernel) -> {start,end} bucket table -> bounding boxes of every aligned run of 32
+//     ("chunk") and 1024 ("super") sorted points.
+//   * query kernel: one warp per query, persistent CTAs with a dynamic batch counter.
+//     Lane p<27 evaluates probe p's hash and table entry; candidates are streamed 32 at
+//     a time with one coalesced float4 load per lane; the K best d^2 live one per lane
+//     in a register (two for K>32) and are maintained with ballot + shfl.
+//   * EXACT pruning: the reference's result only depends on the multiset of the K
+//     smallest distances among the probed buckets' contents (A.1 step 7).  A chunk whose
+//     box lower bound -- evaluated with the same monotone float32 op sequence as d^2 --
+//     is >= the current K-th best can never contribute, so it is skipped.  Big buckets
+//     (the clustered part of the cloud, where the reference visits 10^4..10^5 candidates
+//     per point) are walked super -> chunk -> points, nearest box first (redux.min).
+//     Selection is done on d^2 and sqrt is taken of the K winners only (sqrt is
+//     monotone, so the K smallest d are the sqrt of the K smallest d^2).
+//   * reference quirks kept on purpose: hash buckets (not cells), a bucket reached by two
+//     probes is scanned twice, int32-wrapping probe hash (GSX_HASH_I32WRAP), self/duplicate
+//     skip by d^2 > 1e-12, K capped at 50, 1e10 "empty" sentinel and the < 0.9e10 validity
+//     test, mean = 0 when no candidate was found.
+#include "gsx_common.cuh"
+#include "gsx_sor.cuh"
+
+#include <cub/device/device_radix_sort.cuh>
+#include <math.h>
+
+namespace gsx {
+
+// smallest float32 whose sqrt is >= 1e10f: d is inserted by the reference iff sqrt(d2) < 1e10f
+#define GSX_D2LIM_BITS 0x60ad78ebu
+#define GSX_FULL 0xffffffffu
+
+constexpr int kMortonBits = 18;
+constexpr int kSmallBucket = 64;  // buckets up to this size are scanned without box tests
+constexpr int kQueryBatch = 16;   // consecutive queries grabbed per warp
+
+// ------------------------------------------------------------------ workspace layout
+
+SorWs sor_carve(void* ws, int64_t ws_bytes, int64_t n, size_t cub_bytes) {
+    SorWs w;
+    Carver c(ws, (size_t)ws_bytes);
+    int64_t nchunk = (n + 31) / 32, nsuper = (nchunk + 31) / 32;
+    w.n = n;
+    w.keys0 = c.take<uint64_t>(n);
+    w.keys1 = c.take<uint64_t>(n);
+    w.vals0 = c.take<int32_t>(n);
+    w.vals1 = c.take<int32_t>(n);
+    w.spos = c.take<float4>(n);
+    w.table = c.take<int2>(n);
+    w.caabb = c.take<float4>(2 * nchunk);
+    w.saabb = c.take<float4>(2 * nsuper);
+    w.partial = c.take<float>(6 * 1024);
+    w.minmax = c.take<float>(8);
+    w.counters = c.take<unsigned int>(64);
+    w.stats = c.take<unsigned long long>(8);
+    w.meanstd = c.take<float>(8);
+    w.cub_bytes = cub_bytes;
+    w.cub_temp = c.take<char>(cub_bytes);
+    w.ms_bytes = mean_std_ws_bytes(n);
+    w.ms_ws = c.take<char>(w.ms_bytes);
+    w.total = align_up(c.off, 256);
+    w.ok = c.ok();
+    return w;
+}
+
+size_t sor_cub_bytes(int64_t n) {
+    size_t bytes = 0;
+    cub::DoubleBuffer<uint64_t> k(nullptr, nullptr);
+    cub::DoubleBuffer<int32_t> v(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, (int)n, 0, 50, (cudaStream_t)0);
+    return bytes + 256;
+}
+
+int64_t sor_workspace_bytes(int64_t n) {
+    if (n < 1) n = 1;
+    SorWs w = sor_carve(nullptr, 0, n, sor_cub_bytes(n));
+    return (int64_t)w.total + 1024;
+}
+
+// ------------------------------------------------------------------ min / max
+
+__global__ void __launch_bounds__(256) k_minmax_partial(const float* __restrict__ xyz, int64_t n,
+                                                        float* __restrict__ partial) {
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float v = xyz[3 * i + a];
+            lo[a] = fminf(lo[a], v);
+            hi[a] = fmaxf(hi[a], v);
+        }
+    }
+    __shared__ float sm[6][8];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(GSX_FULL, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(GSX_FULL, hi[a], o));
+        }
+        if (lane_id() == 0) {
+            sm[a][threadIdx.x >> 5] = lo[a];
+            sm[3 + a][threadIdx.x >> 5] = hi[a];
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float r = sm[threadIdx.x][0];
+        for (int w = 1; w < 8; ++w) r = threadIdx.x < 3 ? fminf(r, sm[threadIdx.x][w]) : fmaxf(r, sm[threadIdx.x][w]);
+        partial[blockIdx.x * 6 + threadIdx.x] = r;
+    }
+}
+
+__global__ void k_minmax_final(const float* __restrict__ partial, int nblocks, float* __restrict__ out) {
+    int a = threadIdx.x;
+    if (a < 6) {
+        float r = partial[a];
+        for (int b = 1; b < nblocks; ++b) r = a < 3 ? fminf(r, partial[b * 6 + a]) : fmaxf(r, partial[b * 6 + a]);
+        out[a] = r;
+    }
+}
+
+int sor_minmax(const float* xyz, int64_t n, float* minmax_dev, float* partial, cudaStream_t st) {
+    int blocks = (int)((n + 255) / 256);
+    int cap = sm_count() * 4;
+    if (blocks > cap) blocks = cap;
+    if (blocks > 1024) blocks = 1024;
+    if (blocks < 1) blocks = 1;
+    k_minmax_partial<<<blocks, 256, 0, st>>>(xyz, n, partial);
+    GSX_KERNEL_CHECK();
+    k_minmax_final<<<1, 32, 0, st>>>(partial, blocks, minmax_dev);
+    GSX_KERNEL_CHECK();
+    return GSX_OK;
+}
+
+// ------------------------------------------------------------------ keys
+
+__device__ __forceinline__ uint32_t spread6(uint32_t v) {  // 6 bits -> every third bit
+    v &= 63u;
+    v = (v | (v << 8)) & 0x0000300Fu;   // ..xx........xxxx
+    v = (v | (v << 4)) & 0x000030C3u;   // ..xx....xx....xx
+    v = (v | (v << 2)) & 0x00009249u;   // x..x..x..x..x..x
+    return v;
+}
+
+// gpu_ops.py:216-224: gi = floor((p - min)/cell) (float32 ops), int64 hash mod n.
+__global__ void __launch_bounds__(256) k_sor_keys(const float* __restrict__ xyz, int64_t n, float bx, float by,
+                                                  float bz, float cell, uint64_t* __restrict__ keys,
+                                                  int32_t* __restrict__ vals) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float fx = __fdiv_rn(__fsub_rn(xyz[3 * i], bx), cell);
+    float fy = __fdiv_rn(__fsub_rn(xyz[3 * i + 1], by), cell);
+    float fz = __fdiv_rn(__fsub_rn(xyz[3 * i + 2], bz), cell);
+    float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+    int64_t gx = (int64_t)(int32_t)flx, gy = (int64_t)(int32_t)fly, gz = (int64_t)(int32_t)flz;
+    int64_t h = ((gx * 73856093LL) ^ (gy * 19349663LL) ^ (gz * 83492791LL)) % n;
+    if (h < 0) h += n;
+    // position inside the cell, 6 bits per axis (ordering only -- never affects results)
+    uint32_t sx = (uint32_t)fminf(63.f, fmaxf(0.f, (fx - flx) * 64.f));
+    uint32_t sy = (uint32_t)fminf(63.f, fmaxf(0.f, (fy - fly) * 64.f));
+    uint32_t sz = (uint32_t)fminf(63.f, fmaxf(0.f, (fz - flz) * 64.f));
+    uint32_t mort = (spread6(sx) << 2) | (spread6(sy) << 1) | spread6(sz);
+    keys[i] = ((uint64_t)h << kMortonBits) | (uint64_t)mort;
+    vals[i] = (int32_t)i;
+}
+
+// gpu_ops.py:232-237: first index and size of every bucket.  table pre-zeroed: {0,0} = empty
+// (the reference's cell_start == -1 <=> cell_count == 0).
+__global__ void __launch_bounds__(256) k_sor_table(const uint64_t* __restrict__ keys, int64_t n,
+                                                   int2* __restrict__ table) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    uint32_t h = (uint32_t)(keys[j] >> kMortonBits);
+    if (j == 0 || (uint32_t)(keys[j - 1] >> kMortonBits) != h) table[h].x = (int)j;
+    if (j == n - 1 || (uint32_t)(keys[j + 1] >> kMortonBits) != h) table[h].y = (int)(j + 1);
+}
+
+// gpu_ops.py:228: sorted_pos = pos[sort_order], as float4 with w = original index; plus the boxes.
+// One block = 1024 sorted points = one "super", one warp = one chunk.
+__global__ void __launch_bounds__(1024) k_sor_gather(const float* __restrict__ xyz, const int32_t* __restrict__ order,
+                                                     int64_t n, float4* __restrict__ spos, float4* __restrict__ caabb,
+                                                     float4* __restrict__ saabb) {
+    int64_t j = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (j < n) {
+        int32_t idx = order[j];
+        float x = xyz[3 * (int64_t)idx], y = xyz[3 * (int64_t)idx + 1], z = xyz[3 * (int64_t)idx + 2];
+        spos[j] = make_float4(x, y, z, __int_as_float(idx));
+        lo[0] = hi[0] = x;
+        lo[1] = hi[1] = y;
+        lo[2] = hi[2] = z;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(GSX_FULL, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(GSX_FULL, hi[a], o));
+        }
+    __shared__ float sm[6][32];
+    int w = threadIdx.x >> 5;
+    int64_t chunk = (int64_t)blockIdx.x * 32 + w;
+    if (lane_id() == 0) {
+        if (chunk * 32 < n) {
+            caabb[2 * chunk] = make_float4(lo[0], lo[1], lo[2], hi[0]);
+            caabb[2 * chunk + 1] = make_float4(hi[1], hi[2], 0.f, 0.f);
+        }
+        for (int a = 0; a < 3; ++a) {
+            sm[a][w] = lo[a];
+            sm[3 + a][w] = hi[a];
+        }
+    }
+    __syncthreads();
+    if (w == 0) {
+        float v[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            v[a] = sm[a][lane_id()];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                float t = __shfl_xor_sync(GSX_FULL, v[a], o);
+                v[a] = a < 3 ? fminf(v[a], t) : fmaxf(v[a], t);
+            }
+        }
+        if (lane_id() == 0) {
+            saabb[2 * (int64_t)blockIdx.x] = make_float4(v[0], v[1], v[2], v[3]);
+            saabb[2 * (int64_t)blockIdx.x + 1] = make_float4(v[4], v[5], 0.f, 0.f);
+        }
+    }
+}
+
+int sor_build(const float* xyz, int64_t n, const float* bmin, float cell, SorWs& w, cudaStream_t st) {
+    int blocks = (int)((n + 255) / 256);
+    k_sor_keys<<<blocks, 256, 0, st>>>(xyz, n, bmin[0], bmin[1], bmin[2], cell, w.keys0, w.vals0);
+    GSX_KERNEL_CHECK();
+    int hash_bits = 1;
+    while (((int64_t)1 << hash_bits) < n) ++hash_bits;
+    cub::DoubleBuffer<uint64_t> kb(w.keys0, w.keys1);
+    cub::DoubleBuffer<int32_t> vb(w.vals0, w.vals1);
+    size_t tb = w.cub_bytes;
+    GSX_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(w.cub_temp, tb, kb, vb, (int)n, 0, kMortonBits + hash_bits, st));
+    w.keys_sorted = kb.Current();
+    w.order = vb.Current();
+    GSX_CUDA_CHECK(cudaMemsetAsync(w.table, 0, (size_t)n * sizeof(int2), st));
+    k_sor_table<<<blocks, 256, 0, st>>>(w.keys_sorted, n, w.table);
+    GSX_KERNEL_CHECK();
+    k_sor_gather<<<(int)((n + 1023) / 1024), 1024, 0, st>>>(xyz, w.order, n, w.spos, w.caabb, w.saabb);
+    GSX_KERNEL_CHECK();
+    return GSX_OK;
+}
+
+// ------------------------------------------------------------------ query kernel
+
+// gpu_ops.py:130-132 probe hash.  mode 0: int32 wrapping products (Taichi default_ip), Python-style
+// modulo via Lemire fastmod; mode 1: int64 products.
+__device__ __forceinline__ uint32_t probe_hash(int nx, int ny, int nz, uint32_t n, uint64_t M, int mode) {
+    if (mode == GSX_HASH_MODE_I32WRAP) {
+        int32_t h = (int32_t)((uint32_t)nx * 73856093u) ^ (int32_t)((uint32_t)ny * 19349663u) ^
+                    (int32_t)((uint32_t)nz * 83492791u);
+        uint32_t a = h < 0 ? (uint32_t)(-(int64_t)h) : (uint32_t)h;
+        uint32_t r = fastmod_u32(a, M, n);
+        return h < 0 ? (r ? n - r : 0u) : r;
+    } else {
+        int64_t h = ((int64_t)nx * 73856093LL) ^ ((int64_t)ny * 19349663LL) ^ ((int64_t)nz * 83492791LL);
+        int64_t r = h % (int64_t)n;
+        if (r < 0) r += n;
+        return (uint32_t)r;
+    }
+}
+
+// Lower bound of the float32 d^2 the scan would compute for any point inside the box: same op
+// sequence (sub, mul, add -- no fma), every op monotone, so lb <= d2(point) exactly.
+__device__ __forceinline__ float box_lb(const float4* __restrict__ aabb, int64_t id, float qx, float qy, float qz) {
+    float4 a = __ldg(aabb + 2 * id), b = __ldg(aabb + 2 * id + 1);
+    float dx = fmaxf(fmaxf(__fsub_rn(a.x, qx), __fsub_rn(qx, a.w)), 0.f);
+    float dy = fmaxf(fmaxf(__fsub_rn(a.y, qy), __fsub_rn(qy, b.x)), 0.f);
+    float dz = fmaxf(fmaxf(__fsub_rn(a.z, qz), __fsub_rn(qz, b.y)), 0.f);
+    return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+}
+
+template <int NREG>
+struct TopK {
+    float v0, v1;  // lane l holds rank l (v0) and rank 32+l (v1) of the ascending d^2 list
+    float tau;     // current K-th smallest (rank K-1), warp-uniform
+    int K;
+    __device__ __forceinline__ void init(int k) {
+        K = k;
+        v0 = v1 = tau = __uint_as_float(GSX_D2LIM_BITS);
+    }
+    // insert warp-uniform x (< tau), gpu_ops.py:154-160 in the d^2 domain
+    __device__ __forceinline__ void insert(float x, int lane) {
+        float up0 = __shfl_up_sync(GSX_FULL, v0, 1);
+        if (NREG == 2) {
+            float top0 = __shfl_sync(GSX_FULL, v0, 31);
+            float up1 = __shfl_up_sync(GSX_FULL, v1, 1);
+            if (lane == 0) up1 = top0;
+            if (v1 > x) v1 = fmaxf(up1, x);
+        }
+        if (lane == 0) up0 = 0.f;
+        if (v0 > x) v0 = fmaxf(up0, x);
+        tau = (NREG == 2 && K > 32) ? __shfl_sync(GSX_FULL, v1, K - 33) : __shfl_sync(GSX_FULL, v0, K - 1);
+    }
+};
+
+// distance of the query to candidate j and ballot/shfl insertion of the lanes that beat tau
+template <int NREG, bool STATS>
+__device__ __forceinline__ void scan32(const float4* __restrict__ spos, int64_t j, bool valid, float qx, float qy,
+                                       float qz, TopK<NREG>& tk, int lane, unsigned long long& n_scanned) {
+    float d2 = INFINITY;
+    if (valid) {
+        float4 c = __ldg(spos + j);
+        float ax = __fsub_rn(qx, c.x), ay = __fsub_rn(qy, c.y), az = __fsub_rn(qz, c.z);
+        d2 = __fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az));
+    }
+    if (STATS) n_scanned += __popc(__ballot_sync(GSX_FULL, valid));
+    bool pass = valid && d2 > 1.0e-12f && d2 < tk.tau;
+    unsigned m = __ballot_sync(GSX_FULL, pass);
+    while (m) {
+        int src = __ffs(m) - 1;
+        m &= m - 1;
+        float x = __shfl_sync(GSX_FULL, d2, src);
+        if (x < tk.tau) tk.insert(x, lane);
+    }
+}
+
+template <int NREG, bool STATS>
+__global__ void __launch_bounds__(256)
+    k_sor_knn(const float4* __restrict__ spos, const int2* __restrict__ table, const float4* __restrict__ caabb,
+              const float4* __restrict__ saabb, float* __restrict__ final_means, unsigned int* __restrict__ work,
+              int64_t q_begin, int64_t q_end, int K, int hash_mode, float bx, float by, float bz, float cell,
+              uint32_t n, uint64_t M, unsigned long long* __restrict__ stats) {
+    const int lane = lane_id();
+    unsigned long long st_visits = 0, st_scanned = 0, st_boxes = 0, st_queries = 0;
+    // probe offsets of lane p<27 in the reference's loop order (dx outer, dz inner)
+    const int pdx = lane / 9 - 1, pdy = (lane / 3) % 3 - 1, pdz = lane % 3 - 1;
+
+    for (;;) {
+        unsigned int b0 = 0;
+        if (lane == 0) b0 = atomicAdd(work, (unsigned)kQueryBatch);
+        b0 = __shfl_sync(GSX_FULL, b0, 0);
+        int64_t qb = q_begin + (int64_t)b0;
+        if (qb >= q_end) break;
+        int64_t qe = qb + kQueryBatch < q_end ? qb + kQueryBatch : q_end;
+        for (int64_t i = qb; i < qe; ++i) {
+            const float4 q = __ldg(spos + i);
+            const int gx = (int)floorf(__fdiv_rn(__fsub_rn(q.x, bx), cell));
+            const int gy = (int)floorf(__fdiv_rn(__fsub_rn(q.y, by), cell));
+            const int gz = (int)floorf(__fdiv_rn(__fsub_rn(q.z, bz), cell));
+            int ps = 0, pc = 0;
+            if (lane < 27) {
+                uint32_t h = probe_hash(gx + pdx, gy + pdy, gz + pdz, n, M, hash_mode);
+                int2 t = __ldg(table + h);
+                ps = t.x;
+                pc = t.y - t.x;
+            }
+            if (STATS) {
+                int tot = pc;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(GSX_FULL, tot, o);
+                st_visits += (unsigned long long)tot;
+                st_queries += 1;
+            }
+            TopK<NREG> tk;
+            tk.init(K);
+
+            // seed from the chunk that holds the query itself when its own bucket is big: gives a
+            // tight tau before the box walk.  Only legal if the centre probe really reaches the
+            // query's bucket range (with the wrapped hash it may not).
+            int skip_chunk = -1;
+            {
+                int s13 = __shfl_sync(GSX_FULL, ps, 13), c13 = __shfl_sync(GSX_FULL, pc, 13);
+                if (c13 > kSmallBucket && i >= s13 && i < (int64_t)s13 + c13) {
+                    skip_chunk = (int)(i >> 5);
+                    int64_t j = ((int64_t)skip_chunk << 5) + lane;
+                    scan32<NREG, STATS>(spos, j, j >= s13 && j < (int64_t)s13 + c13, q.x, q.y, q.z, tk, lane,
+                                        st_scanned);
+                }
+            }
+
+            for (int pi = 0; pi < 27; ++pi) {
+                const int p = pi == 0 ? 13 : (pi <= 13 ? pi - 1 : pi);  // centre first
+                const int s = __shfl_sync(GSX_FULL, ps, p), c = __shfl_sync(GSX_FULL, pc, p);
+                if (c <= 0) continue;
+                const int64_t e = (int64_t)s + c;
+                if (c <= kSmallBucket) {
+                    for (int64_t base = s; base < e; base += 32)
+                        scan32<NREG, STATS>(spos, base + lane, base + lane < e, q.x, q.y, q.z, tk, lane, st_scanned);
+                    continue;
+                }
+                const int skip = p == 13 ? skip_chunk : -1;
+                const int fc = s >> 5, lc = (int)((e - 1) >> 5);
+                const int fs = fc >> 5, ls = lc >> 5;
+                for (int sb = fs; sb <= ls; sb += 32) {
+                    const int sid = sb + lane;
+                    unsigned skey = 0xffffffffu;
+                    if (sid <= ls) {
+                        float lb = box_lb(saabb, sid, q.x, q.y, q.z);
+                        if (lb < tk.tau) skey = __float_as_uint(lb);
+                    }
+                    if (STATS) st_boxes += __popc(__ballot_sync(GSX_FULL, sid <= ls));
+                    for (;;) {
+                        unsigned ms = __reduce_min_sync(GSX_FULL, skey);
+                        if (ms == 0xffffffffu || !(__uint_as_float(ms) < tk.tau)) break;
+                        int srcs = __ffs(__ballot_sync(GSX_FULL, skey == ms)) - 1;
+                        if (lane == srcs) skey = 0xffffffffu;
+                        const int sup = sb + srcs;
+                        const int cid = sup * 32 + lane;
+                        const bool cv = cid >= fc && cid <= lc && cid != skip;
+                        unsigned ckey = 0xffffffffu;
+                        if (cv) {
+                            float lb = box_lb(caabb, cid, q.x, q.y, q.z);
+                            if (lb < tk.tau) ckey = __float_as_uint(lb);
+                        }
+                        if (STATS) st_boxes += __popc(__ballot_sync(GSX_FULL, cv));
+                        for (;;) {
+                            unsigned mc = __reduce_min_sync(GSX_FULL, ckey);
+                            if (mc == 0xffffffffu || !(__uint_as_float(mc) < tk.tau)) break;
+                            int srcc = __ffs(__ballot_sync(GSX_FULL, ckey == mc)) - 1;
+                            if (lane == srcc) ckey = 0xffffffffu;
+                            int64_t j = ((int64_t)(sup * 32 + srcc) << 5) + lane;
+                            scan32<NREG, STATS>(spos, j, j >= s && j < e, q.x, q.y, q.z, tk, lane, st_scanned);
+                        }
+                    }
+                }
+            }
+
+            // gpu_ops.py:163-174: ascending serial float32 sum of the valid (< 0.9e10) distances
+            float d0 = __fsqrt_rn(tk.v0), d1 = NREG == 2 ? __fsqrt_rn(tk.v1) : 0.f;
+            float sum = 0.f;
+            int valid = 0;
+            for (int r = 0; r < K; ++r) {
+                float x = (NREG == 2 && r >= 32) ? __shfl_sync(GSX_FULL, d1, r - 32) : __shfl_sync(GSX_FULL, d0, r);
+                if (x < 0.9e10f) {
+                    sum = __fadd_rn(sum, x);
+                    ++valid;
+                }
+            }
+            if (lane == 0) final_means[__float_as_int(q.w)] = valid > 0 ? __fdiv_rn(sum, (float)valid) : 0.f;
+        }
+    }
+    if (STATS && lane == 0) {
+        atomicAdd(stats + 0, st_visits);
+        atomicAdd(stats + 1, st_scanned);
+        atomicAdd(stats + 2, st_boxes);
+        atomicAdd(stats + 3, st_queries);
+    }
+}
+
+__global__ void k_fill_f32(float* p, int64_t n, float v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+int sor_mean_dists(SorWs& w, int64_t q_begin, int64_t q_end, int k, int hash_mode, const float* bmin, float cell,
+                   float* final_means, unsigned long long* stats, cudaStream_t st) {
+    int64_t n = w.n;
+    GSX_REQUIRE(k >= 1, GSX_ERR_ARG, "sor: k must be >= 1 (got %d)", k);
+    GSX_REQUIRE(hash_mode == 0 || hash_mode == 1, GSX_ERR_ARG, "sor: bad hash_mode %d", hash_mode);
+    GSX_REQUIRE(q_begin >= 0 && q_end <= n && q_begin <= q_end, GSX_ERR_ARG, "sor: bad query range");
+    int K = k < 50 ? k : 50;  // gpu_ops.py:244
+    if (q_end == q_begin) return GSX_OK;
+    if (!(cell > 1e-8f)) {  // gpu_ops.py:175-176 (unreachable through the driver: cell >= 1e-4)
+        GSX_REQUIRE(q_begin == 0 && q_end == n, GSX_ERR_UNSUPPORTED, "sor: degenerate cell with a query range");
+        k_fill_f32<<<(int)((n + 255) / 256), 256, 0, st>>>(final_means, n, 0.f);
+        GSX_KERNEL_CHECK();
+        return GSX_OK;
+    }
+    GSX_CUDA_CHECK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned int), st));
+    uint64_t M = 0xFFFFFFFFFFFFFFFFull / (uint64_t)n + 1ull;
+    int64_t nq = q_end - q_begin;
+    int64_t want = (nq + (int64_t)kQueryBatch * 8 - 1) / ((int64_t)kQueryBatch * 8);
+    int grid = sm_count() * 8;  // 8 CTAs x 8 warps = 64 resident warps per SM
+    if ((int64_t)grid > want) grid = (int)want;
+    if (grid < 1) grid = 1;
+#define GSX_LAUNCH_KNN(NREG, STATS)                                                                              \
+    k_sor_knn<NREG, STATS><<<grid, 256, 0, st>>>(w.spos, w.table, w.caabb, w.saabb, final_means, w.counters,      \
+                                                 q_begin, q_end, K, hash_mode, bmin[0], bmin[1], bmin[2], cell, \
+                                                 (uint32_t)n, M, stats)
+    if (stats) {
+        if (K <= 32) GSX_LAUNCH_KNN(1, true); else GSX_LAUNCH_KNN(2, true);
+    } else {
+        if (K <= 32) GSX_LAUNCH_KNN(1, false); else GSX_LAUNCH_KNN(2, false);
+    }
+    GSX_KERNEL_CHECK();
+    return GSX_OK;
+}
+
+}  // namespace gsx

@@ -1,0 +1,43 @@
+// gsx_sor.cuh -- internal declarations shared by the SOR translation units and the C ABI.
+#pragma once
+#include "gsx_common.cuh"
+
+#define GSX_HASH_MODE_I32WRAP 0
+#define GSX_HASH_MODE_I64 1
+
+namespace gsx {
+
+struct SorWs {
+    int64_t n;
+    uint64_t *keys0, *keys1, *keys_sorted;
+    int32_t *vals0, *vals1, *order;
+    float4* spos;   // hash-sorted positions, w = original index
+    int2* table;    // bucket -> {start, end} in sorted order ({0,0} = empty)
+    float4* caabb;  // 2 float4 per 32-point chunk: {lo.x,lo.y,lo.z,hi.x},{hi.y,hi.z,-,-}
+    float4* saabb;  // same per 1024-point super
+    float* partial;
+    float* minmax;
+    unsigned int* counters;
+    unsigned long long* stats;
+    float* meanstd;
+    char* cub_temp;
+    size_t cub_bytes;
+    char* ms_ws;
+    size_t ms_bytes;
+    size_t total;
+    bool ok;
+};
+
+SorWs sor_carve(void* ws, int64_t ws_bytes, int64_t n, size_t cub_bytes);
+int64_t sor_workspace_bytes(int64_t n);
+size_t sor_cub_bytes(int64_t n);
+int sor_minmax(const float* xyz, int64_t n, float* minmax_dev, float* partial, cudaStream_t st);
+int sor_build(const float* xyz, int64_t n, const float* bmin, float cell, SorWs& w, cudaStream_t st);
+int sor_mean_dists(SorWs& w, int64_t q_begin, int64_t q_end, int k, int hash_mode, const float* bmin, float cell,
+                   float* final_means, unsigned long long* stats, cudaStream_t st);
+
+size_t mean_std_ws_bytes(int64_t n);
+int mean_std_f32(const float* a, int64_t n, float* out_dev, void* ws, size_t ws_bytes, cudaStream_t st);
+int threshold_mask(const float* a, int64_t n, const float* meanstd_dev, float tf, uint8_t* mask, cudaStream_t st);
+
+}  // namespace gsx

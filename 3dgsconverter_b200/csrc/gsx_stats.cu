@@ -1,0 +1,200 @@
+// gsx_stats.cu -- np.mean / np.std of a float32 vector, bit-for-bit, on device; threshold mask.
+//
+// Replaces gpu_ops.py:259-263 and data_processor.py:176-180 (glob_mean/glob_std/threshold/mask).
+// NumPy reduces float32 with float32 accumulators in a fixed *pairwise* order:
+//   n < 8      : serial
+//   n <= 128   : 8 interleaved accumulators, ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), serial tail
+//   otherwise  : split at n2 = n/2 - (n/2)%8, sum(left) + sum(right)
+// The split tree depends only on n, so it parallelises exactly: one thread per leaf block walks the
+// tree from the root along the bits of its slot index, sums its <=128 elements in NumPy's order, and
+// the inner nodes are then combined bottom-up in place (left + right, one float add per node).
+#include "gsx_common.cuh"
+#include "gsx_sor.cuh"
+
+#include <set>
+
+namespace gsx {
+
+static int pairwise_depth(int64_t n) {
+    std::set<int64_t> level{n};
+    int d = 0;
+    for (;;) {
+        std::set<int64_t> next;
+        for (int64_t m : level)
+            if (m > 128) {
+                int64_t n2 = m / 2;
+                n2 -= n2 % 8;
+                next.insert(n2);
+                next.insert(m - n2);
+            }
+        if (next.empty()) return d;
+        // leaves (<=128) at this depth stay where they are; only split nodes go deeper
+        level.swap(next);
+        ++d;
+    }
+}
+
+size_t mean_std_ws_bytes(int64_t n) {
+    if (n < 1) n = 1;
+    int d = pairwise_depth(n);
+    return (((size_t)1 << d) + 64) * sizeof(float);
+}
+
+// walk from the root `depth` levels along the bits of `path` (MSB first).  Returns false if the
+// walk hits a leaf (size <= 128) before `depth` levels; else sets (off, m) of the node reached.
+__device__ __forceinline__ bool walk(int64_t n, int depth, uint32_t path, int64_t& off, int64_t& m, int& reached) {
+    off = 0;
+    m = n;
+    for (int l = 0; l < depth; ++l) {
+        if (m <= 128) {
+            reached = l;
+            return false;
+        }
+        int64_t n2 = m / 2;
+        n2 -= n2 % 8;
+        if ((path >> (depth - 1 - l)) & 1u) {
+            off += n2;
+            m -= n2;
+        } else {
+            m = n2;
+        }
+    }
+    reached = depth;
+    return true;
+}
+
+template <bool SQ>
+__device__ __forceinline__ float elem(const float* __restrict__ a, int64_t i, float mean) {
+    float v = a[i];
+    if (SQ) {
+        float t = __fsub_rn(v, mean);
+        v = __fmul_rn(t, t);
+    }
+    return v;
+}
+
+template <bool SQ>
+__global__ void __launch_bounds__(128) k_pw_leaves(const float* __restrict__ a, int64_t n, int dmax,
+                                                   const float* __restrict__ meanp, float* __restrict__ slot) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (1u << dmax)) return;
+    int64_t off, m;
+    int reached;
+    bool full = walk(n, dmax, t, off, m, reached);
+    if (!full) {
+        // a leaf at depth `reached` < dmax: owned by the slot whose remaining low bits are zero
+        if (t & ((1u << (dmax - reached)) - 1u)) return;
+    }
+    const float mean = SQ ? meanp[0] : 0.f;
+    float res;
+    if (m < 8) {
+        res = 0.f;
+        for (int64_t i = 0; i < m; ++i) res = __fadd_rn(res, elem<SQ>(a, off + i, mean));
+    } else {
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = elem<SQ>(a, off + j, mean);
+        int64_t i;
+        for (i = 8; i < m - (m % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], elem<SQ>(a, off + i + j, mean));
+        }
+        res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        for (; i < m; ++i) res = __fadd_rn(res, elem<SQ>(a, off + i, mean));
+    }
+    slot[t] = res;
+}
+
+// combine the nodes of depth d: node u = left(u) + right(u), in place at the left child's slot
+__device__ __forceinline__ void combine_node(int64_t n, int dmax, int d, uint32_t u, float* slot) {
+    int64_t off, m;
+    int reached;
+    if (!walk(n, d, u, off, m, reached)) return;  // no such node (an ancestor is a leaf)
+    if (m <= 128) return;                         // a leaf: already final
+    size_t li = (size_t)u << (dmax - d);
+    size_t ri = ((size_t)(2 * u + 1)) << (dmax - d - 1);
+    slot[li] = __fadd_rn(slot[li], slot[ri]);
+}
+
+__global__ void __launch_bounds__(256) k_pw_level(int64_t n, int dmax, int d, float* slot) {
+    uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < (1u << d)) combine_node(n, dmax, d, u, slot);
+}
+
+// levels dtop..0 in one block, then the final division (and sqrt for the variance pass)
+template <bool SQ>
+__global__ void __launch_bounds__(1024) k_pw_top(int64_t n, int dmax, int dtop, float* slot, float* out) {
+    for (int d = dtop; d >= 0; --d) {
+        if (threadIdx.x < (1u << d)) combine_node(n, dmax, d, threadIdx.x, slot);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        float v = __fdiv_rn(slot[0], __ll2float_rn((long long)n));
+        if (SQ) out[1] = __fsqrt_rn(v);
+        else out[0] = v;
+    }
+}
+
+template <bool SQ>
+static int pairwise_pass(const float* a, int64_t n, int dmax, float* slot, float* out, cudaStream_t st) {
+    uint32_t leaves = 1u << dmax;
+    k_pw_leaves<SQ><<<(leaves + 127) / 128, 128, 0, st>>>(a, n, dmax, out, slot);
+    GSX_KERNEL_CHECK();
+    int d = dmax - 1;
+    for (; d > 9; --d) {
+        k_pw_level<<<((1u << d) + 255) / 256, 256, 0, st>>>(n, dmax, d, slot);
+        GSX_KERNEL_CHECK();
+    }
+    k_pw_top<SQ><<<1, 1024, 0, st>>>(n, dmax, d, slot, out);  // d may be -1 (single leaf): loop is skipped
+    GSX_KERNEL_CHECK();
+    return GSX_OK;
+}
+
+int mean_std_f32(const float* a, int64_t n, float* out_dev, void* ws, size_t ws_bytes, cudaStream_t st) {
+    GSX_REQUIRE(n >= 1, GSX_ERR_ARG, "mean_std: n must be >= 1");
+    GSX_REQUIRE(ws_bytes >= mean_std_ws_bytes(n), GSX_ERR_WORKSPACE, "mean_std: workspace too small");
+    int dmax = pairwise_depth(n);
+    GSX_REQUIRE(dmax <= 31, GSX_ERR_UNSUPPORTED, "mean_std: n too large");
+    float* slot = (float*)ws;
+    int rc = pairwise_pass<false>(a, n, dmax, slot, out_dev, st);
+    if (rc) return rc;
+    return pairwise_pass<true>(a, n, dmax, slot, out_dev, st);
+}
+
+// gpu_ops.py:261-263: thresh = mean + f32(tf) * std (float32 mul then add), mask = a < thresh
+__global__ void __launch_bounds__(256) k_threshold_mask(const float* __restrict__ a, int64_t n,
+                                                        const float* __restrict__ ms, float tf,
+                                                        uint8_t* __restrict__ mask) {
+    const float thresh = __fadd_rn(ms[0], __fmul_rn(tf, ms[1]));
+    int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        float4 v = *reinterpret_cast<const float4*>(a + i);
+        uchar4 o = make_uchar4(v.x < thresh, v.y < thresh, v.z < thresh, v.w < thresh);
+        *reinterpret_cast<uchar4*>(mask + i) = o;
+    } else {
+        for (; i < n; ++i) mask[i] = a[i] < thresh;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_threshold_mask_scalar(const float* __restrict__ a, int64_t n,
+                                                               const float* __restrict__ ms, float tf,
+                                                               uint8_t* __restrict__ mask) {
+    const float thresh = __fadd_rn(ms[0], __fmul_rn(tf, ms[1]));
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) mask[i] = a[i] < thresh;
+}
+
+int threshold_mask(const float* a, int64_t n, const float* meanstd_dev, float tf, uint8_t* mask, cudaStream_t st) {
+    if (n == 0) return GSX_OK;
+    if (((uintptr_t)a % 16 == 0) && ((uintptr_t)mask % 4 == 0)) {
+        int64_t nv = (n + 3) / 4;
+        k_threshold_mask<<<(int)((nv + 255) / 256), 256, 0, st>>>(a, n, meanstd_dev, tf, mask);
+    } else {
+        k_threshold_mask_scalar<<<(int)((n + 255) / 256), 256, 0, st>>>(a, n, meanstd_dev, tf, mask);
+    }
+    GSX_KERNEL_CHECK();
+    return GSX_OK;
+}
+
+}  // namespace gsx

@@ -1,0 +1,130 @@
+/*
+ * gsx.h -- C ABI of libgsx.so, the B200-native (sm_100a) backend for the per-point
+ * filtering + codebook clustering hot path of francescofugazzi/3dgsconverter.
+ *
+ * The reference has no FFI of its own (it is pure Python + Taichi); the boundary it
+ * exposes is the Python module surface gsconverter.processing.{gpu_ops,data_processor}.
+ * Each entry point below names the reference interface it replaces (path:line relative
+ * to /root/reference/gsconverter/).  INTEGRATION.md shows the ctypes binding.
+ *
+ * Conventions
+ *   - plain C types only; device pointers are ordinary pointers into CUDA device
+ *     memory of the *current* device; `stream` is a cudaStream_t passed as void*
+ *     (NULL = default stream).
+ *   - every function returns 0 on success, <0 on error (GSX_ERR_*); the message is
+ *     available from gsx_last_error() (thread-local).  The Python wrapper turns a
+ *     non-zero status into an exception, which preserves the reference's
+ *     "GPU exception => caller falls back" convention (data_processor.py:146-153,
+ *     gpu_ops.py:40-46).
+ *   - the library never owns device memory in the *_device entry points: the caller
+ *     provides outputs and one scratch blob whose size comes from *_workspace_bytes.
+ *     The *_host convenience entry points take host buffers and manage device memory
+ *     internally (cudaMallocAsync), copies included.
+ *   - all masks are uint8 (0/1), one byte per point, like numpy bool.
+ *   - N < 2^31 - 64 (int32 indices, as in gpu_ops.py:224,233-234).
+ */
+#ifndef GSX_H
+#define GSX_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSX_HASH_I32WRAP 0 /* probe hash with wrapping int32 products: Taichi default_ip (faithful) */
+#define GSX_HASH_I64 1     /* probe hash with int64 products: what the host table build uses (intended) */
+
+/* ---- library ---------------------------------------------------------------------- */
+const char* gsx_last_error(void);
+int gsx_version(void);          /* 100*major + minor */
+int gsx_device_sm_count(void);  /* SMs of the current device (grid sizing), <0 on error */
+
+/* ---- SOR, Taichi semantics: gpu_ops.py:193-263 (filter_sor_gpu) + :98-176 (kernel) - */
+
+/* Scratch needed by gsx_sor_filter_device / the gsx_sor_* stages for n points. */
+int64_t gsx_sor_workspace_bytes(int64_t n);
+
+/* gpu_ops.py:203-204: per-axis min/max of xyz[n,3] -> minmax_dev[6] = {minx,miny,minz,maxx,maxy,maxz}. */
+int gsx_sor_minmax(const float* xyz_dev, int64_t n, float* minmax_dev, void* ws, int64_t ws_bytes, void* stream);
+
+/* gpu_ops.py:205-213 on the host (NumPy-2 float32 semantics, powf).  minmax is a HOST array of 6. */
+float gsx_sor_cell_size(const float* minmax_host, int64_t n);
+
+/* gpu_ops.py:216-237: grid index, int64 hash mod n, sort by bucket, bucket table.  Fills the
+ * workspace with the hash-sorted float4 positions (w = original index), the bucket table and the
+ * 32-/1024-point bounding boxes used for exact pruning.  bmin = the 3 minima, cell = cell size. */
+int gsx_sor_build(const float* xyz_dev, int64_t n, const float* bmin_host, float cell, void* ws, int64_t ws_bytes,
+                  void* stream);
+
+/* gpu_ops.py:98-176 + :255-256: K = min(k,50) nearest candidates over the 27 probed buckets, mean of
+ * their distances, written in the caller's point order (the "unsort" is fused).  Must follow
+ * gsx_sor_build on the same workspace.  hash_mode = GSX_HASH_*.  stats_dev (may be NULL) receives
+ * 4 uint64 counters {reference-model visits V, candidates actually scanned, box tests, queries}. */
+int gsx_sor_mean_dists(int64_t n, int32_t k, int32_t hash_mode, const float* bmin_host, float cell, void* ws,
+                       int64_t ws_bytes, float* final_means_dev, unsigned long long* stats_dev, void* stream);
+
+/* Multi-GPU variant: only the hash-sorted positions [q_begin, q_end) are queried; the rows of
+ * final_means_dev belonging to other queries are left untouched (caller zero-fills and all-reduces). */
+int gsx_sor_mean_dists_range(int64_t n, int64_t q_begin, int64_t q_end, int32_t k, int32_t hash_mode,
+                             const float* bmin_host, float cell, void* ws, int64_t ws_bytes, float* final_means_dev,
+                             unsigned long long* stats_dev, void* stream);
+
+/* gpu_ops.py:259-260 / data_processor.py:176-177: np.mean and np.std of a float32 vector with
+ * float32 accumulators and NumPy's pairwise summation order, bit-for-bit.  out_dev[0]=mean, [1]=std. */
+int64_t gsx_mean_std_workspace_bytes(int64_t n);
+int gsx_mean_std_f32(const float* a_dev, int64_t n, float* out_dev, void* ws, int64_t ws_bytes, void* stream);
+
+/* gpu_ops.py:261-263 / data_processor.py:178-180: mask[i] = a[i] < mean + f32(threshold_factor)*std. */
+int gsx_threshold_mask(const float* a_dev, int64_t n, const float* meanstd_dev, float threshold_factor,
+                       uint8_t* mask_dev, void* stream);
+
+/* Whole filter on device buffers (one 24-byte D2H sync inside for the cell size).
+ * means_dev may be NULL.  Equivalent of filter_sor_gpu(data, k, threshold_factor). */
+int gsx_sor_filter_device(const float* xyz_dev, int64_t n, int32_t k, float threshold_factor, int32_t hash_mode,
+                          uint8_t* mask_dev, float* means_dev, void* ws, int64_t ws_bytes, void* stream);
+
+/* Whole filter on HOST buffers: the binding target for gpu_ops.filter_sor_gpu (gpu_ops.py:193).
+ * xyz_host float32[n,3]; mask_host uint8[n]; means_host float32[n] or NULL. */
+int gsx_sor_filter_host(const float* xyz_host, int64_t n, int32_t k, float threshold_factor, int32_t hash_mode,
+                        uint8_t* mask_host, float* means_host);
+
+/* ---- bbox / alpha masks: data_processor.py:215-231, :184-213 ------------------------ */
+/* keep <=> lo <= v <= hi on all axes, float32 compares (bounds already rounded to float32 by caller). */
+int gsx_bbox_mask(const float* xyz_dev, int64_t n, const float* lohi_host /*[6]*/, uint8_t* mask_dev, void* stream);
+/* keep <=> (double)opacity >= logit_thresh (float64 compare, data_processor.py:208). */
+int gsx_alpha_mask(const float* opacity_dev, int64_t n, double logit_thresh, uint8_t* mask_dev, void* stream);
+/* host helper: data_processor.py:203-205 -> logit threshold for min_opacity_u8 in (0,255). */
+double gsx_alpha_logit_threshold(double min_opacity_u8);
+
+/* ---- density filter: data_processor.py:38-52 (voxel histogram) and :111-112 (member mask) ---- */
+int64_t gsx_density_workspace_bytes(int64_t n, int64_t cap);
+/* q = floor(xyz / f32(voxel)) -> int64 triple (data_processor.py:39); counts per voxel (:43); every voxel
+ * with count >= max(min_points,1) (:48-51) is returned to the HOST arrays dense_vox_host (int64[cap,3]) and
+ * dense_cnt_host (int32[cap]), in no particular order; *n_dense_host = how many (> cap => GSX_ERR_WORKSPACE);
+ * *n_voxels_host (may be NULL) = number of distinct voxels (len(unique_voxels), :45). */
+int gsx_density_voxel_count(const float* xyz_dev, int64_t n, float voxel, int64_t min_points, int64_t* dense_vox_host,
+                            int32_t* dense_cnt_host, int64_t cap, int64_t* n_dense_host, int64_t* n_voxels_host,
+                            void* ws, int64_t ws_bytes, void* stream);
+/* data_processor.py:111-112: mask[i] = voxel(point i) is one of the n_keep voxels of keep_vox_host
+ * (HOST int64[n_keep,3], the output of the host-side cluster selection :59-106). */
+int gsx_density_member_mask(const float* xyz_dev, int64_t n, float voxel, const int64_t* keep_vox_host, int64_t n_keep,
+                            uint8_t* mask_dev, void* ws, int64_t ws_bytes, void* stream);
+
+/* ---- K-Means: gpu_ops.py:57-96 (kernels) + :186-188 (Lloyd loop) ---------------------- */
+/* Batched over `nprob` independent problems stored back to back (SOG shN chunks, sog.py:527-549):
+ * problem p has rows [row_off[p], row_off[p+1]) of X[*,D] and K centroids at C[p*K*D].
+ * One call = max_iter x (assign ; update) with the serial index-order float32 sums of SURVEY A.5.
+ * labels are those of the last assign (one update behind C); counts int32[nprob*K]. */
+int64_t gsx_kmeans_workspace_bytes(int64_t n_total, int32_t nprob, int32_t K, int32_t D);
+int gsx_kmeans_lloyd_device(const float* X_dev, const int64_t* row_off_host, int32_t nprob, int32_t K, int32_t D,
+                            int32_t max_iter, float* C_dev, int32_t* labels_dev, int32_t* counts_dev, void* ws,
+                            int64_t ws_bytes, void* stream);
+/* Single problem on HOST buffers: binding target for gpu_ops.kmeans on the GPU path (gpu_ops.py:178-191)
+ * with the init centroids chosen by the caller (the reference's np.random.choice draw). */
+int gsx_kmeans_host(const float* X_host, int64_t n, int32_t K, int32_t D, int32_t max_iter, float* C_host_inout,
+                    int32_t* labels_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSX_H */

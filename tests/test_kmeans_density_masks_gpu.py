@@ -1,0 +1,103 @@
+"""GPU parity for K-Means (bit-exact vs the oracle's serial order), density, bbox and alpha masks."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _kmeans_data(n, d):
+    from gsx import synth
+    at = synth.attributes(n)
+    if d == 1:
+        return np.ascontiguousarray(at["scale"].reshape(-1, 1)[:n])
+    return np.ascontiguousarray(at["f_rest"][:, :d])
+
+
+@pytest.mark.parametrize("n,d,k,it", [(20_000, 45, 64, 5), (50_000, 1, 256, 20), (10_000, 9, 16, 10),
+                                      (10_000, 24, 100, 3), (3_000, 3, 7, 4), (5_000, 5, 33, 3), (4_000, 45, 300, 2)])
+def test_kmeans_matches_oracle(n, d, k, it, cuda, gsx_lib):
+    import torch
+    import oracle
+    from gsx import kmeans as gk
+    X = _kmeans_data(n, d)
+    np.random.seed(1234)
+    init = oracle.kmeans_reference_init(X, k)
+    Co, Lo, cnto = oracle.kmeans_lloyd(X, k, it, init=init)
+    C, L, cnt = gk.kmeans_lloyd(torch.from_numpy(X).to(cuda), k, it, torch.from_numpy(init).to(cuda))
+    assert np.array_equal(L.cpu().numpy(), Lo)
+    assert np.array_equal(cnt.cpu().numpy(), cnto)
+    # contract: 1e-5 relative (north_star); we are bit-identical to the oracle's serial float32 order
+    assert np.array_equal(C.cpu().numpy().view(np.uint32), Co.view(np.uint32))
+    Ch, Lh = gk.kmeans_host(X, k, it, init)
+    assert np.array_equal(Lh, Lo) and np.allclose(Ch, Co, rtol=1e-5, atol=0)
+
+
+def test_kmeans_batched_chunks(cuda, gsx_lib):
+    """The SOG shN schedule: independent chunks in one launch (sog.py:527-549)."""
+    import torch
+    import oracle
+    from gsx import kmeans as gk, synth
+    X = synth.attributes(30_000)["f_rest"]
+    offs = [0, 7_000, 16_001, 30_000]
+    K = 32
+    rng = np.random.default_rng(3)
+    init = np.stack([X[offs[p]:offs[p + 1]][rng.choice(offs[p + 1] - offs[p], K, replace=False)] for p in range(3)])
+    C, L, cnt = gk.kmeans_lloyd_batched(torch.from_numpy(X).to(cuda), offs, K, 4, torch.from_numpy(init).to(cuda))
+    for p in range(3):
+        Co, Lo, cnto = oracle.kmeans_lloyd(X[offs[p]:offs[p + 1]], K, 4, init=init[p])
+        assert np.array_equal(L[offs[p]:offs[p + 1]].cpu().numpy(), Lo)
+        assert np.array_equal(C[p].cpu().numpy().view(np.uint32), Co.view(np.uint32))
+
+
+def test_kmeans_empty_cluster_collapses_to_zero(cuda, gsx_lib):
+    import torch
+    import oracle
+    from gsx import kmeans as gk
+    X = np.r_[np.zeros((50, 2)), np.ones((50, 2))].astype(np.float32)
+    init = np.array([[0, 0], [1, 1], [50, 50]], np.float32)  # third centroid attracts nothing
+    Co, Lo, cnto = oracle.kmeans_lloyd(X, 3, 2, init=init)
+    C, L, cnt = gk.kmeans_lloyd(torch.from_numpy(X).to(cuda), 3, 2, torch.from_numpy(init).to(cuda))
+    assert cnto[2] == 0 and np.all(Co[2] == 0)
+    assert np.array_equal(C.cpu().numpy(), Co) and np.array_equal(L.cpu().numpy(), Lo)
+
+
+@pytest.mark.parametrize("n", [1000, 100_000, 1_000_000])
+@pytest.mark.parametrize("sens,multi", [(0.1, False), (0.5, True), (0.5, False), (0.9, True)])
+def test_density_matches_oracle(n, sens, multi, cuda, gsx_lib):
+    import torch
+    import oracle
+    from gsx import density, synth
+    xyz = synth.xyz(n, "mixed")
+    want, info_o = oracle.density_mask(xyz, sensitivity=sens, keep_multicluster=multi)
+    got, info = density.density_filter(torch.from_numpy(xyz).to(cuda), sensitivity=sens, keep_multicluster=multi)
+    assert info["clusters"] == info_o["clusters"] and info["max_len"] == info_o["max_len"]
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_density_explicit_params_and_hash_path(cuda, gsx_lib):
+    import torch
+    import oracle
+    from gsx import density
+    rng = np.random.default_rng(2)
+    # far-flung sparse cloud: voxel grid too large for the dense histogram -> hash-table path
+    xyz = np.r_[rng.normal(0, 1, (20_000, 3)), rng.uniform(-5e4, 5e4, (2_000, 3))].astype(np.float32)
+    for vs, thr, multi in ((0.5, 0.05, True), (0.1, 0.0, False), (2.0, 1.0, False)):
+        want, _ = oracle.density_mask(xyz, voxel_size=vs, threshold_percentage=thr, keep_multicluster=multi)
+        got, _ = density.density_filter(torch.from_numpy(xyz).to(cuda), vs, thr, keep_multicluster=multi)
+        assert np.array_equal(got.cpu().numpy(), want), (vs, thr, multi)
+
+
+def test_bbox_alpha_match_oracle(cuda, gsx_lib):
+    import torch
+    import oracle
+    from gsx import masks, synth
+    for n in (1, 3, 1001, 200_000):
+        xyz = synth.xyz(n, "mixed")
+        op = synth.attributes(n)["opacity"]
+        x = torch.from_numpy(xyz).to(cuda)
+        for box in ((-2, -2, -2, 2, 2, 2), (-11, -11, -11, 11, 11, 11), (0.1, -0.3, 0.7, 0.1000001, 5, 9)):
+            want = oracle.bbox_mask(xyz[:, 0], xyz[:, 1], xyz[:, 2], *box)
+            assert np.array_equal(masks.bbox_mask(x, *box).cpu().numpy(), want)
+        o = torch.from_numpy(op).to(cuda)
+        for m in (1, 5, 128, 254):
+            assert np.array_equal(masks.alpha_mask(o, m).cpu().numpy(), oracle.alpha_mask(op, m))

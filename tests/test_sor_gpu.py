@@ -1,0 +1,93 @@
+"""GPU parity: SOR (Taichi semantics) through the C ABI vs the CPU oracle -- bit-exact.
+
+Reference path under test: gpu_ops.py:193-263 (+ kernel :98-176).  Bar: final_means and the
+keep-mask identical bit for bit (integer/index work and IEEE float32 with a fixed op order).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(xyz_np, k, sigma, mode, cuda):
+    import torch
+    from gsx import sor
+    x = torch.from_numpy(xyz_np).to(cuda)
+    mask, means = sor.sor_filter(x, k, sigma, hash_mode=mode, return_means=True)
+    return mask.cpu().numpy(), means.cpu().numpy()
+
+
+@pytest.mark.parametrize("kind", ["mixed", "uniform", "clustered"])
+@pytest.mark.parametrize("mode", ["i32wrap", "i64"])
+@pytest.mark.parametrize("n,k", [(100_000, 16), (100_000, 27), (30_000, 50), (300_000, 16)])
+def test_sor_matches_oracle(kind, mode, n, k, cuda, gsx_lib):
+    import oracle
+    from gsx import synth
+    xyz = synth.xyz(n, kind)
+    want = oracle.sor_taichi_mean_dists(xyz, k, mode)
+    for sigma in (2.0,):
+        mask, means = _run(xyz, k, sigma, mode, cuda)
+        assert np.array_equal(means.view(np.uint32), want.view(np.uint32)), \
+            f"mean dists differ at {np.flatnonzero(means != want)[:5]}"
+        assert np.array_equal(mask, oracle.threshold_mask(want, sigma))
+
+
+@pytest.mark.parametrize("mode", ["i32wrap", "i64"])
+def test_sor_1m_mixed_wrapped_hash_diverges(mode, cuda, gsx_lib):
+    """At 1 M points the grid exceeds the int32-safe range: i32wrap != i64 and both must match."""
+    import oracle
+    from gsx import synth
+    xyz = synth.xyz(1_000_000, "mixed")
+    want = oracle.sor_taichi_mean_dists(xyz, 16, mode)
+    mask, means = _run(xyz, 16, 2.0, mode, cuda)
+    assert np.array_equal(means.view(np.uint32), want.view(np.uint32))
+    removed = int((~mask).sum())
+    assert removed == {"i32wrap": 15932, "i64": 1385}[mode]  # SURVEY §8(c) anchor counts
+
+
+def test_sor_edge_cases(cuda, gsx_lib):
+    import oracle
+    rng = np.random.default_rng(5)
+    cases = {
+        "tiny": rng.normal(size=(5, 3)),
+        "single": np.zeros((1, 3)),
+        "all_same": np.ones((100, 3)),
+        "planar": np.c_[rng.uniform(-1, 1, (5000, 2)), np.zeros(5000)],
+        "duplicates": np.repeat(rng.normal(size=(500, 3)), 4, axis=0),
+        "line": np.c_[np.linspace(0, 1, 2000), np.zeros(2000), np.zeros(2000)],
+        "two_blobs_far": np.r_[rng.normal(0, 0.01, (3000, 3)), rng.normal(1000, 0.01, (3000, 3))],
+        "big_bucket": rng.normal(0, 1e-3, (20000, 3)),
+    }
+    for name, pts in cases.items():
+        xyz = pts.astype(np.float32)
+        for k in (3, 16):
+            for mode in ("i32wrap", "i64"):
+                want = oracle.sor_taichi_mean_dists(xyz, k, mode)
+                mask, means = _run(xyz, k, 1.0, mode, cuda)
+                assert np.array_equal(means.view(np.uint32), want.view(np.uint32)), (name, k, mode)
+                assert np.array_equal(mask, oracle.threshold_mask(want, 1.0)), (name, k, mode)
+
+
+def test_sor_host_entry_and_errors(cuda, gsx_lib):
+    import oracle
+    from gsx import sor, synth, GsxError
+    xyz = synth.xyz(50_000, "mixed")
+    mask, means = sor.sor_filter_host(xyz, 16, 2.0, return_means=True)
+    want = oracle.sor_taichi_mean_dists(xyz, 16, "i32wrap")
+    assert np.array_equal(means.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(mask, oracle.threshold_mask(want, 2.0))
+    with pytest.raises(ValueError):
+        sor.sor_filter_host(np.zeros((10, 2), np.float32))
+    with pytest.raises(GsxError):
+        sor.sor_filter_host(xyz, 0, 1.0)
+
+
+def test_mean_std_matches_numpy(cuda, gsx_lib):
+    import torch
+    from gsx import sor
+    rng = np.random.default_rng(11)
+    for n in (1, 5, 8, 9, 27, 100, 128, 129, 1000, 4097, 100_003, 3_000_001):
+        a = rng.gamma(2.0, 0.3, n).astype(np.float32)
+        got = sor.mean_std(torch.from_numpy(a).to(cuda)).cpu().numpy()
+        want = np.array([np.mean(a), np.std(a)], dtype=np.float32)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), n
