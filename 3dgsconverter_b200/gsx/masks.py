@@ -21,7 +21,11 @@ def bbox_mask(xyz: torch.Tensor, min_x, min_y, min_z, max_x, max_y, max_z) -> to
 
 
 def alpha_logit_threshold(min_opacity_u8) -> float:
-    return float(lib.gsx_alpha_logit_threshold(float(min_opacity_u8)))
+    """data_processor.py:203-205, evaluated by NumPy itself: np.log's float64 SIMD loop may differ from
+    libm by an ulp, and the reference's threshold is whatever NumPy returns on this host.
+    (gsx_alpha_logit_threshold is the libm version for non-Python FFI clients.)"""
+    a = np.clip(min_opacity_u8 / 255.0, 1e-6, 1.0 - 1e-6)
+    return float(np.log(a / (1.0 - a)))
 
 
 def alpha_mask(opacity: torch.Tensor, min_opacity_u8) -> torch.Tensor:

@@ -93,7 +93,8 @@ int gsx_sor_filter_host(const float* xyz_host, int64_t n, int32_t k, float thres
 int gsx_bbox_mask(const float* xyz_dev, int64_t n, const float* lohi_host /*[6]*/, uint8_t* mask_dev, void* stream);
 /* keep <=> (double)opacity >= logit_thresh (float64 compare, data_processor.py:208). */
 int gsx_alpha_mask(const float* opacity_dev, int64_t n, double logit_thresh, uint8_t* mask_dev, void* stream);
-/* host helper: data_processor.py:203-205 -> logit threshold for min_opacity_u8 in (0,255). */
+/* host helper: data_processor.py:203-205 -> logit threshold for min_opacity_u8 in (0,255), libm log
+ * (NumPy's SIMD log may differ by one float64 ulp; the Python plugin passes NumPy's own value). */
 double gsx_alpha_logit_threshold(double min_opacity_u8);
 
 /* ---- density filter: data_processor.py:38-52 (voxel histogram) and :111-112 (member mask) ---- */
