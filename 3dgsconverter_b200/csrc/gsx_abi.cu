@@ -10,6 +10,7 @@
 #include "gsx_masks.cuh"
 #include "gsx_sor.cuh"
 
+#include <atomic>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -18,6 +19,9 @@
 namespace gsx {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -65,6 +69,7 @@ extern "C" {
 
 const char* gsx_last_error(void) { return g_err; }
 int gsx_version(void) { return 100; }
+long long gsx_kernel_launches(void) { return g_launches.load(); }
 int gsx_device_sm_count(void) {
     int dev = 0, v = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return GSX_ERR_CUDA;

@@ -17,6 +17,7 @@
 namespace gsx {
 
 void set_error(const char* fmt, ...);
+void count_launch();
 
 #define GSX_CUDA_CHECK(expr)                                                                  \
     do {                                                                                      \
@@ -27,7 +28,12 @@ void set_error(const char* fmt, ...);
         }                                                                                     \
     } while (0)
 
-#define GSX_KERNEL_CHECK() GSX_CUDA_CHECK(cudaGetLastError())
+// follows every launch of one of OUR kernels: counts it (gsx_kernel_launches) and checks the launch
+#define GSX_KERNEL_CHECK()                    \
+    do {                                      \
+        gsx::count_launch();                  \
+        GSX_CUDA_CHECK(cudaGetLastError());   \
+    } while (0)
 
 #define GSX_REQUIRE(cond, code, ...)   \
     do {                               \

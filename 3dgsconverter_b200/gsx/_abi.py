@@ -33,6 +33,7 @@ _SIGS = {
     "gsx_last_error": (C.c_char_p, []),
     "gsx_version": (C.c_int, []),
     "gsx_device_sm_count": (C.c_int, []),
+    "gsx_kernel_launches": (C.c_longlong, []),
     "gsx_sor_workspace_bytes": (_i64, [_i64]),
     "gsx_sor_minmax": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp]),
     "gsx_sor_cell_size": (C.c_float, [_f32p, _i64]),

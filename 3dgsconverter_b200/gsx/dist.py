@@ -1,0 +1,94 @@
+"""Multi-GPU (one process per GPU, torch.distributed) versions of the hot path.
+
+SOR (Taichi semantics) is global by construction: the bucket table is a hash of size N_global, so a
+halo exchange cannot reproduce it.  Scheme: every rank holds a slab of the cloud;
+  1. all-gather of the float32 xyz slabs (12 B/pt over NVLink),
+  2. every rank builds the full hash grid (replicated, ~5 % of the query cost),
+  3. rank r queries the r-th contiguous range of hash-sorted positions (neighbouring queries share
+     buckets, so the range split keeps cache locality) and writes mean distances at the original indices
+     of a zero-filled vector,
+  4. ONE all-reduce(sum) of that vector -- every entry is written by exactly one rank, so x+0 is exact --
+  5. the bit-exact NumPy-order mean/std and the threshold run replicated; each rank keeps its slab's mask.
+The result is bit-identical to the single-GPU filter on the concatenated cloud.
+
+K-Means (SOG chunks) shards by problem: chunks are independent, no data-path collective.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class _GsxOps:
+    """Device ops used by the sharded drivers (replaceable in CPU/gloo tests)."""
+
+    def build(self, xyz_all):
+        from . import sor
+        return sor.build_grid(xyz_all)
+
+    def mean_dists_range(self, grid, k, hash_mode, out, qb, qe):
+        from . import sor
+        sor.mean_dists(grid, k, hash_mode, out=out, q_range=(qb, qe))
+
+    def mask_from_means(self, means, threshold_factor):
+        from . import sor
+        return sor.threshold_mask(means, sor.mean_std(means), threshold_factor)
+
+
+def _all_gather_rows(x: torch.Tensor, group=None):
+    """All-gather a [n_local, C] tensor with possibly different n_local per rank."""
+    world = dist.get_world_size(group)
+    n_local = torch.tensor([x.shape[0]], dtype=torch.int64, device=x.device)
+    sizes = [torch.zeros_like(n_local) for _ in range(world)]
+    dist.all_gather(sizes, n_local, group=group)
+    sizes = [int(s.item()) for s in sizes]
+    if len(set(sizes)) == 1:
+        out = torch.empty((world * sizes[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+        return out, sizes
+    mx = max(sizes)
+    pad = torch.zeros((mx,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    pad[: x.shape[0]] = x
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([p[:s] for p, s in zip(parts, sizes)], dim=0), sizes
+
+
+def query_range(n_total: int, rank: int, world: int):
+    """Contiguous split of the hash-sorted query positions."""
+    return (n_total * rank) // world, (n_total * (rank + 1)) // world
+
+
+def sor_filter_sharded(xyz_local: torch.Tensor, k: int = 25, threshold_factor: float = 1.0,
+                       hash_mode: str | None = None, group=None, return_means: bool = False, ops=None):
+    """SOR keep-mask of this rank's slab, bit-identical to the single-GPU filter on the union cloud."""
+    ops = ops or _GsxOps()
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    xyz_all, sizes = _all_gather_rows(xyz_local, group)
+    n = xyz_all.shape[0]
+    grid = ops.build(xyz_all)
+    qb, qe = query_range(n, rank, world)
+    means = torch.zeros(n, dtype=torch.float32, device=xyz_all.device)
+    ops.mean_dists_range(grid, k, hash_mode, means, qb, qe)
+    dist.all_reduce(means, op=dist.ReduceOp.SUM, group=group)
+    mask_all = ops.mask_from_means(means, threshold_factor)
+    off = sum(sizes[:rank])
+    sl = slice(off, off + sizes[rank])
+    return (mask_all[sl], means[sl]) if return_means else mask_all[sl]
+
+
+def kmeans_chunks_sharded(X_chunks, K: int, max_iter: int, inits, group=None, runner=None):
+    """SOG shN schedule across ranks: chunk p goes to rank p % world; no collective on the data path.
+    X_chunks / inits: lists (only the entries owned by this rank need to be real tensors).
+    Returns {chunk index: (C, labels, counts)} for the chunks this rank owns."""
+    from . import kmeans as gk
+    runner = runner or gk.kmeans_lloyd
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    out = {}
+    for p in range(len(X_chunks)):
+        if p % world == rank:
+            out[p] = runner(X_chunks[p], K, max_iter, inits[p])
+    return out

@@ -38,6 +38,8 @@ extern "C" {
 const char* gsx_last_error(void);
 int gsx_version(void);          /* 100*major + minor */
 int gsx_device_sm_count(void);  /* SMs of the current device (grid sizing), <0 on error */
+long long gsx_kernel_launches(void); /* cumulative number of gsx kernels launched by this process (CUB's sort
+                                        kernels inside gsx_sor_build are not counted) */
 
 /* ---- SOR, Taichi semantics: gpu_ops.py:193-263 (filter_sor_gpu) + :98-176 (kernel) - */
 

@@ -1,0 +1,93 @@
+"""CPU, world_size 2, gloo: the sharded SOR driver (gsx/dist.py) reproduces the single-process
+result bit for bit.  Device ops are replaced by the CPU oracle here (test only)."""
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+class OracleOps:
+    """Stand-in for the CUDA ops so the collective logic can run on CPU."""
+
+    def build(self, xyz_all):
+        import oracle
+        pos = xyz_all.numpy()
+        lo, cell = oracle.sor_cell_size(pos)
+        from oracle.sor import sor_hash_table
+        order, cs, cc = sor_hash_table(pos, lo, cell)
+        return dict(pos=pos, lo=lo, cell=cell, order=order, cs=cs, cc=cc)
+
+    def mean_dists_range(self, grid, k, hash_mode, out, qb, qe):
+        import ctypes
+        import oracle
+        from oracle import _p
+        n = len(grid["pos"])
+        spos = np.ascontiguousarray(grid["pos"][grid["order"]])
+        md = np.zeros(n, np.float32)
+        oracle.lib().orc_sor_mean_dists(_p(spos, ctypes.c_float), _p(grid["cs"], ctypes.c_int32),
+                                        _p(grid["cc"], ctypes.c_int32), _p(md, ctypes.c_float), float(grid["lo"][0]),
+                                        float(grid["lo"][1]), float(grid["lo"][2]), ctypes.c_float(grid["cell"]), n, n,
+                                        min(k, 50), {"i32wrap": 0, "i64": 1}[hash_mode or "i32wrap"], None)
+        o = out.numpy()
+        o[grid["order"][qb:qe]] = md[qb:qe]   # only this rank's range of sorted positions
+
+    def mask_from_means(self, means, threshold_factor):
+        import oracle
+        return torch.from_numpy(oracle.threshold_mask(means.numpy(), threshold_factor))
+
+
+def _worker(rank, world, port, sizes, q):
+    sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "3dgsconverter_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gsx import dist as gd, synth
+    xyz = synth.xyz(sum(sizes), "mixed")
+    off = sum(sizes[:rank])
+    local = torch.from_numpy(xyz[off:off + sizes[rank]].copy())
+    mask, means = gd.sor_filter_sharded(local, 16, 2.0, "i32wrap", return_means=True, ops=OracleOps())
+    q.put((rank, mask.numpy(), means.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("sizes", [(20_000, 20_000), (25_000, 15_001)])
+def test_sor_sharded_equals_single(sizes):
+    import oracle
+    from gsx import synth
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, sizes, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict()
+    for _ in range(2):
+        r, m, md = q.get(timeout=300)
+        res[r] = (m, md)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    xyz = synth.xyz(sum(sizes), "mixed")
+    want = oracle.sor_taichi_mean_dists(xyz, 16, "i32wrap")
+    wmask = oracle.threshold_mask(want, 2.0)
+    got = np.concatenate([res[0][1], res[1][1]])
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(np.concatenate([res[0][0], res[1][0]]), wmask)
+
+
+def test_query_range_partition():
+    from gsx.dist import query_range
+    for n in (1, 7, 1000, 10_000_019):
+        for w in (1, 2, 4, 8):
+            edges = [query_range(n, r, w) for r in range(w)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(w - 1))
