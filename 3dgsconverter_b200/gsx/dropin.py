@@ -1,0 +1,57 @@
+"""Put the gsx backend behind an already-installed 3dgsconverter without touching its files.
+
+    import gsx.dropin; gsx.dropin.patch()      # before running gsconverter.main / Converter
+
+Replaces, in the *installed* ``gsconverter.processing`` package (converter.py:10,150 and
+formats/sog.py:11 import from there):
+  * ``gpu_ops.kmeans``, ``gpu_ops.filter_sor_gpu``, ``gpu_ops.HAS_TAICHI``
+  * the filter methods of ``DataProcessor`` (crop_by_bbox, apply_alpha_filter, apply_density_filter,
+    remove_flyers)
+Host-only helpers and everything else of the reference stay as they are.
+"""
+from __future__ import annotations
+
+import importlib
+import importlib.util
+import sys
+from pathlib import Path
+
+_HERE = Path(__file__).resolve().parent.parent
+
+
+def _load_ours(modname: str, relpath: str):
+    spec = importlib.util.spec_from_file_location(modname, _HERE / relpath,
+                                                  submodule_search_locations=None)
+    mod = importlib.util.module_from_spec(spec)
+    return spec, mod
+
+
+def patch(verbose: bool = False):
+    ref_gpu_ops = importlib.import_module("gsconverter.processing.gpu_ops")
+    ref_dp = importlib.import_module("gsconverter.processing.data_processor")
+    if getattr(ref_gpu_ops, "_GSX_PATCHED", False):
+        return
+    # load our two modules under private names but with the reference's package as parent, so their
+    # relative imports (..utils.utility_functions) resolve to the installed reference
+    ours = {}
+    for name, rel in (("gpu_ops", "gsconverter/processing/gpu_ops.py"),
+                      ("data_processor", "gsconverter/processing/data_processor.py")):
+        full = f"gsconverter.processing._gsx_{name}"
+        spec = importlib.util.spec_from_file_location(full, _HERE / rel)
+        mod = importlib.util.module_from_spec(spec)
+        mod.__package__ = "gsconverter.processing"
+        sys.modules[full] = mod
+        ours[name] = (spec, mod)
+    ours["gpu_ops"][0].loader.exec_module(ours["gpu_ops"][1])
+    g = ours["gpu_ops"][1]
+    ref_gpu_ops.kmeans = g.kmeans
+    ref_gpu_ops.filter_sor_gpu = g.filter_sor_gpu
+    ref_gpu_ops.HAS_TAICHI = g.HAS_TAICHI
+    ref_gpu_ops._GSX_PATCHED = True
+    # our data_processor does `from .gpu_ops import ...`: that now resolves to the patched reference module
+    ours["data_processor"][0].loader.exec_module(ours["data_processor"][1])
+    Ours = ours["data_processor"][1].DataProcessor
+    for meth in ("crop_by_bbox", "apply_alpha_filter", "apply_density_filter", "remove_flyers"):
+        setattr(ref_dp.DataProcessor, meth, getattr(Ours, meth))
+    if verbose:
+        print("[gsx] gsconverter.processing patched: SOR / density / bbox / alpha / K-Means run on libgsx.so")
