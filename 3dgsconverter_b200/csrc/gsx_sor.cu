@@ -288,6 +288,23 @@ __device__ __forceinline__ float box_lb(const float4* __restrict__ aabb, int64_t
     return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
+// one compare-exchange stage of a 32-lane bitonic network: lanes whose `take_min` is set keep the
+// smaller of (own, partner), the others the larger
+__device__ __forceinline__ float cmpx(float v, int j, bool take_min) {
+    float o = __shfl_xor_sync(GSX_FULL, v, j);
+    return take_min ? fminf(v, o) : fmaxf(v, o);
+}
+
+// ascending bitonic sort of one value per lane (15 stages)
+__device__ __forceinline__ float warp_sort32(float v, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) v = cmpx(v, j, ((lane & k) == 0) == ((lane & j) == 0));
+    }
+    return v;
+}
+
 template <int NREG>
 struct TopK {
     float v0, v1;  // lane l holds rank l (v0) and rank 32+l (v1) of the ascending d^2 list
@@ -296,6 +313,9 @@ struct TopK {
     __device__ __forceinline__ void init(int k) {
         K = k;
         v0 = v1 = tau = __uint_as_float(GSX_D2LIM_BITS);
+    }
+    __device__ __forceinline__ void refresh_tau() {
+        tau = (NREG == 2 && K > 32) ? __shfl_sync(GSX_FULL, v1, K - 33) : __shfl_sync(GSX_FULL, v0, K - 1);
     }
     // insert warp-uniform x (< tau), gpu_ops.py:154-160 in the d^2 domain
     __device__ __forceinline__ void insert(float x, int lane) {
@@ -308,9 +328,27 @@ struct TopK {
         }
         if (lane == 0) up0 = 0.f;
         if (v0 > x) v0 = fmaxf(up0, x);
-        tau = (NREG == 2 && K > 32) ? __shfl_sync(GSX_FULL, v1, K - 33) : __shfl_sync(GSX_FULL, v0, K - 1);
+        refresh_tau();
+    }
+    // NREG==1 only: merge one candidate per lane (nv; lanes without a candidate pass the sentinel) into
+    // the list.  sort(nv) ascending, reverse it, lane-wise min with the ascending list = the 32 smallest
+    // of the union as a bitonic sequence, 5 merge stages sort it.  Lanes >= K only ever hold values
+    // >= rank K-1, so they never change the K smallest (only the multiset of values matters, A.1-7).
+    __device__ __forceinline__ void merge32(float nv, int lane) {
+        nv = warp_sort32(nv, lane);
+        float r = __shfl_sync(GSX_FULL, nv, 31 - lane);
+        float m = fminf(v0, r);
+#pragma unroll
+        for (int j = 16; j > 0; j >>= 1) m = cmpx(m, j, (lane & j) == 0);
+        v0 = m;
+        refresh_tau();
     }
 };
+
+#ifndef GSX_MERGE_THRESHOLD
+#define GSX_MERGE_THRESHOLD 9
+#endif
+constexpr int kMergeThreshold = GSX_MERGE_THRESHOLD;  // serial insert ~11 instr each vs ~95 for a full merge
 
 // distance of the query to candidate j and ballot/shfl insertion of the lanes that beat tau
 template <int NREG, bool STATS>
@@ -325,6 +363,10 @@ __device__ __forceinline__ void scan32(const float4* __restrict__ spos, int64_t 
     if (STATS) n_scanned += __popc(__ballot_sync(GSX_FULL, valid));
     bool pass = valid && d2 > 1.0e-12f && d2 < tk.tau;
     unsigned m = __ballot_sync(GSX_FULL, pass);
+    if (NREG == 1 && __popc(m) >= kMergeThreshold) {
+        tk.merge32(pass ? d2 : __uint_as_float(GSX_D2LIM_BITS), lane);
+        return;
+    }
     while (m) {
         int src = __ffs(m) - 1;
         m &= m - 1;
@@ -333,8 +375,11 @@ __device__ __forceinline__ void scan32(const float4* __restrict__ spos, int64_t 
     }
 }
 
+#ifndef GSX_KNN_MINBLOCKS
+#define GSX_KNN_MINBLOCKS 6
+#endif
 template <int NREG, bool STATS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
     k_sor_knn(const float4* __restrict__ spos, const int2* __restrict__ table, const float4* __restrict__ caabb,
               const float4* __restrict__ saabb, float* __restrict__ final_means, unsigned int* __restrict__ work,
               int64_t q_begin, int64_t q_end, int K, int hash_mode, float bx, float by, float bz, float cell,
@@ -351,17 +396,31 @@ __global__ void __launch_bounds__(256)
         int64_t qb = q_begin + (int64_t)b0;
         if (qb >= q_end) break;
         int64_t qe = qb + kQueryBatch < q_end ? qb + kQueryBatch : q_end;
+        // the 27 probes of a query depend only on its cell: consecutive hash-sorted queries mostly share
+        // it, so the hashes and table entries are recomputed only when the cell changes
+        int cgx = 0x7fffffff, cgy = 0, cgz = 0;
+        int ps = 0, pc = 0;
+        unsigned live = 0;  // probes with a non-empty bucket
+#pragma unroll 1
         for (int64_t i = qb; i < qe; ++i) {
             const float4 q = __ldg(spos + i);
             const int gx = (int)floorf(__fdiv_rn(__fsub_rn(q.x, bx), cell));
             const int gy = (int)floorf(__fdiv_rn(__fsub_rn(q.y, by), cell));
             const int gz = (int)floorf(__fdiv_rn(__fsub_rn(q.z, bz), cell));
-            int ps = 0, pc = 0;
-            if (lane < 27) {
-                uint32_t h = probe_hash(gx + pdx, gy + pdy, gz + pdz, n, M, hash_mode);
-                int2 t = __ldg(table + h);
-                ps = t.x;
-                pc = t.y - t.x;
+#ifndef GSX_CELL_REUSE
+#define GSX_CELL_REUSE 1
+#endif
+            // (vote makes the predicate provably warp-uniform: no reconvergence code in the loop below)
+            if (!GSX_CELL_REUSE || __any_sync(GSX_FULL, gx != cgx || gy != cgy || gz != cgz)) {
+                cgx = gx, cgy = gy, cgz = gz;
+                ps = 0, pc = 0;
+                if (lane < 27) {
+                    uint32_t h = probe_hash(gx + pdx, gy + pdy, gz + pdz, n, M, hash_mode);
+                    int2 t = __ldg(table + h);
+                    ps = t.x;
+                    pc = t.y - t.x;
+                }
+                live = __ballot_sync(GSX_FULL, pc > 0);
             }
             if (STATS) {
                 int tot = pc;
@@ -377,7 +436,8 @@ __global__ void __launch_bounds__(256)
             // tight tau before the box walk.  Only legal if the centre probe really reaches the
             // query's bucket range (with the wrapped hash it may not).
             int skip_chunk = -1;
-            {
+            unsigned todo = live;
+            if (todo & (1u << 13)) {
                 int s13 = __shfl_sync(GSX_FULL, ps, 13), c13 = __shfl_sync(GSX_FULL, pc, 13);
                 if (c13 > kSmallBucket && i >= s13 && i < (int64_t)s13 + c13) {
                     skip_chunk = (int)(i >> 5);
@@ -387,12 +447,15 @@ __global__ void __launch_bounds__(256)
                 }
             }
 
-            for (int pi = 0; pi < 27; ++pi) {
-                const int p = pi == 0 ? 13 : (pi <= 13 ? pi - 1 : pi);  // centre first
+#pragma unroll 1
+            while (todo) {
+                // centre bucket first (closest candidates -> tight tau early), then ascending probe index
+                const int p = (todo & (1u << 13)) ? 13 : __ffs(todo) - 1;
+                todo &= ~(1u << p);
                 const int s = __shfl_sync(GSX_FULL, ps, p), c = __shfl_sync(GSX_FULL, pc, p);
-                if (c <= 0) continue;
                 const int64_t e = (int64_t)s + c;
                 if (c <= kSmallBucket) {
+#pragma unroll 1
                     for (int64_t base = s; base < e; base += 32)
                         scan32<NREG, STATS>(spos, base + lane, base + lane < e, q.x, q.y, q.z, tk, lane, st_scanned);
                     continue;
@@ -434,16 +497,15 @@ __global__ void __launch_bounds__(256)
                 }
             }
 
-            // gpu_ops.py:163-174: ascending serial float32 sum of the valid (< 0.9e10) distances
-            float d0 = __fsqrt_rn(tk.v0), d1 = NREG == 2 ? __fsqrt_rn(tk.v1) : 0.f;
+            // gpu_ops.py:163-174: ascending serial float32 sum of the valid (< 0.9e10) distances.  The
+            // list is ascending, so the valid entries are a prefix of the first K ranks.
+            const float d0 = __fsqrt_rn(tk.v0), d1 = NREG == 2 ? __fsqrt_rn(tk.v1) : 0.f;
+            int valid = __popc(__ballot_sync(GSX_FULL, lane < K && d0 < 0.9e10f));
+            if (NREG == 2) valid += __popc(__ballot_sync(GSX_FULL, lane + 32 < K && d1 < 0.9e10f));
             float sum = 0.f;
-            int valid = 0;
-            for (int r = 0; r < K; ++r) {
+            for (int r = 0; r < valid; ++r) {
                 float x = (NREG == 2 && r >= 32) ? __shfl_sync(GSX_FULL, d1, r - 32) : __shfl_sync(GSX_FULL, d0, r);
-                if (x < 0.9e10f) {
-                    sum = __fadd_rn(sum, x);
-                    ++valid;
-                }
+                sum = __fadd_rn(sum, x);
             }
             if (lane == 0) final_means[__float_as_int(q.w)] = valid > 0 ? __fdiv_rn(sum, (float)valid) : 0.f;
         }
@@ -459,6 +521,20 @@ __global__ void __launch_bounds__(256)
 __global__ void k_fill_f32(float* p, int64_t n, float v) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
+}
+
+template <int NREG, bool STATS>
+static int launch_knn(SorWs& w, int64_t q_begin, int64_t q_end, int K, int hash_mode, const float* bmin, float cell,
+                      float* final_means, unsigned long long* stats, uint64_t M, int64_t want, cudaStream_t st) {
+    int per_sm = 0;
+    GSX_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sor_knn<NREG, STATS>, 256, 0));
+    int64_t grid = (int64_t)sm_count() * (per_sm > 0 ? per_sm : 4);  // persistent: exactly the resident CTAs
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    k_sor_knn<NREG, STATS><<<(int)grid, 256, 0, st>>>(w.spos, w.table, w.caabb, w.saabb, final_means, w.counters,
+                                                      q_begin, q_end, K, hash_mode, bmin[0], bmin[1], bmin[2], cell,
+                                                      (uint32_t)w.n, M, stats);
+    return GSX_OK;
 }
 
 int sor_mean_dists(SorWs& w, int64_t q_begin, int64_t q_end, int k, int hash_mode, const float* bmin, float cell,
@@ -479,18 +555,12 @@ int sor_mean_dists(SorWs& w, int64_t q_begin, int64_t q_end, int k, int hash_mod
     uint64_t M = 0xFFFFFFFFFFFFFFFFull / (uint64_t)n + 1ull;
     int64_t nq = q_end - q_begin;
     int64_t want = (nq + (int64_t)kQueryBatch * 8 - 1) / ((int64_t)kQueryBatch * 8);
-    int grid = sm_count() * 8;  // 8 CTAs x 8 warps = 64 resident warps per SM
-    if ((int64_t)grid > want) grid = (int)want;
-    if (grid < 1) grid = 1;
-#define GSX_LAUNCH_KNN(NREG, STATS)                                                                              \
-    k_sor_knn<NREG, STATS><<<grid, 256, 0, st>>>(w.spos, w.table, w.caabb, w.saabb, final_means, w.counters,      \
-                                                 q_begin, q_end, K, hash_mode, bmin[0], bmin[1], bmin[2], cell, \
-                                                 (uint32_t)n, M, stats)
-    if (stats) {
-        if (K <= 32) GSX_LAUNCH_KNN(1, true); else GSX_LAUNCH_KNN(2, true);
-    } else {
-        if (K <= 32) GSX_LAUNCH_KNN(1, false); else GSX_LAUNCH_KNN(2, false);
-    }
+    int rc;
+    if (stats) rc = K <= 32 ? launch_knn<1, true>(w, q_begin, q_end, K, hash_mode, bmin, cell, final_means, stats, M, want, st)
+                            : launch_knn<2, true>(w, q_begin, q_end, K, hash_mode, bmin, cell, final_means, stats, M, want, st);
+    else rc = K <= 32 ? launch_knn<1, false>(w, q_begin, q_end, K, hash_mode, bmin, cell, final_means, stats, M, want, st)
+                      : launch_knn<2, false>(w, q_begin, q_end, K, hash_mode, bmin, cell, final_means, stats, M, want, st);
+    if (rc) return rc;
     GSX_KERNEL_CHECK();
     return GSX_OK;
 }
