@@ -13,10 +13,11 @@
 //     = 2P independent accumulation chains, so the dependent FADD chain of the contract does not
 //     stall the FP32 pipes.  CUDA cores, not tensor cores: the contract's rounding sequence is not
 //     a GEMM (DESIGN.md discusses the GEMM-prefilter idea for a later round).
-//   * update: one warp per (problem, cluster) streams the problem's labels in index order, ballots
-//     the members and accumulates their rows lane-per-dimension.  This reproduces the oracle's
-//     serial index-order sum bit-for-bit and is run-to-run deterministic (the reference's float
-//     atomics are neither); labels are L2-resident, each X row is read once.
+//   * update: a stable partition of the point indices by label (per-warp shared-memory counters,
+//     match.any ranks -- O(N)), then one warp per (problem, cluster) walks its member list in index
+//     order with 8 row loads in flight and accumulates lane-per-dimension.  This reproduces the
+//     oracle's serial index-order float32 sum bit-for-bit and is run-to-run deterministic (the
+//     reference's float atomics are neither).  K > 2047 falls back to a per-cluster label scan.
 #include "gsx_common.cuh"
 #include "gsx_kmeans.cuh"
 
@@ -32,7 +33,11 @@ struct KmProb {
     long long row0;  // first row of the problem in X
     long long rows;  // number of rows
     int tile0;       // first assign tile of the problem
+    int sub0;        // first label sub-tile (kSubTile points, one warp each) of the problem
 };
+
+constexpr int kSubTile = 1024;     // points per warp in the stable label partition
+constexpr int kMaxSortK = 2047;    // clusters (+1 overflow bin) whose per-warp counters fit shared memory
 
 template <int D>
 struct PointsPerThread {
@@ -199,11 +204,225 @@ __global__ void __launch_bounds__(256)
     if (lane == 0) counts[(size_t)p * K + c] = cnt;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Update, O(N) form: a stable partition of the point indices by label, then one warp per cluster
+// walks its member list in index order.  Same sums, bit for bit, as the serial oracle; every phase
+// is deterministic.  hist is [n_subtiles][K+1] (bin K collects label -1 rows, never accumulated).
+
+__device__ __forceinline__ int find_problem_by_sub(const KmProb* __restrict__ probs, int nprob, int sub) {
+    int lo = 0, hi = nprob - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (probs[mid].sub0 <= sub) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// phase 1: per-sub-tile label histogram (one warp per sub-tile, shared-memory counters)
+__global__ void __launch_bounds__(256)
+    k_km_hist(const int* __restrict__ labels, const KmProb* __restrict__ probs, int nprob, int K, int nsub,
+              int* __restrict__ hist) {
+    extern __shared__ int s_cnt[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int sub = blockIdx.x * 8 + w;
+    if (sub >= nsub) return;
+    int* cnt = s_cnt + w * (K + 1);
+    for (int k = lane; k <= K; k += 32) cnt[k] = 0;
+    __syncwarp();
+    const int p = find_problem_by_sub(probs, nprob, sub);
+    const KmProb pr = probs[p];
+    const long long r0 = (long long)(sub - pr.sub0) * kSubTile;
+    const long long r1 = r0 + kSubTile < pr.rows ? r0 + kSubTile : pr.rows;
+    const int* lab = labels + pr.row0;
+    for (long long i = r0 + lane; i < r1; i += 32) {
+        int l = lab[i];
+        atomicAdd(cnt + (l >= 0 && l < K ? l : K), 1);
+    }
+    __syncwarp();
+    for (int k = lane; k <= K; k += 32) hist[(size_t)sub * (K + 1) + k] = cnt[k];
+}
+
+// phase 2: per (problem, cluster) exclusive prefix over the problem's sub-tiles; totals -> counts
+__global__ void __launch_bounds__(256)
+    k_km_scan(const KmProb* __restrict__ probs, int nprob, int K, int nsub_total, int* __restrict__ hist,
+              int* __restrict__ totals) {
+    const int p = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k > K) return;
+    const int s0 = probs[p].sub0;
+    const int s1 = p + 1 < nprob ? probs[p + 1].sub0 : nsub_total;
+    int run = 0;
+#pragma unroll 8
+    for (int sidx = s0; sidx < s1; ++sidx) {
+        size_t at = (size_t)sidx * (K + 1) + k;
+        int v = hist[at];
+        hist[at] = run;
+        run += v;
+    }
+    totals[(size_t)p * (K + 1) + k] = run;
+}
+
+// phase 3: cluster offsets inside the problem (exclusive scan over k of the totals), counts out
+__global__ void k_km_offsets(int nprob, int K, const int* __restrict__ totals, int* __restrict__ offs,
+                             int* __restrict__ counts) {
+    const int p = blockIdx.x;
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    // block-wide scan in strips of blockDim.x
+    for (int base = 0; base <= K; base += blockDim.x) {
+        int k = base + threadIdx.x;
+        int v = k <= K ? totals[(size_t)p * (K + 1) + k] : 0;
+        if (k < K) counts[(size_t)p * K + k] = v;
+        // inclusive warp scan, then scan of warp sums through shared memory
+        int x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            int y = __shfl_up_sync(GSX_FULL, x, o);
+            if ((threadIdx.x & 31) >= o) x += y;
+        }
+        __shared__ int wsum[32];
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int ws = threadIdx.x < (blockDim.x >> 5) ? wsum[threadIdx.x] : 0;
+            for (int o = 1; o < 32; o <<= 1) {
+                int y = __shfl_up_sync(GSX_FULL, ws, o);
+                if (threadIdx.x >= o) ws += y;
+            }
+            wsum[threadIdx.x] = ws;
+        }
+        __syncthreads();
+        int excl = carry + (threadIdx.x >> 5 ? wsum[(threadIdx.x >> 5) - 1] : 0) + x - v;
+        if (k <= K) offs[(size_t)p * (K + 1) + k] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+        __syncthreads();
+    }
+}
+
+// phase 4: stable scatter of the row indices (problem-local) into cluster order
+__global__ void __launch_bounds__(256)
+    k_km_scatter(const int* __restrict__ labels, const KmProb* __restrict__ probs, int nprob, int K, int nsub,
+                 const int* __restrict__ hist, const int* __restrict__ offs, int* __restrict__ member) {
+    extern __shared__ int s_cnt[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int sub = blockIdx.x * 8 + w;
+    if (sub >= nsub) return;
+    int* cnt = s_cnt + w * (K + 1);
+    const int p = find_problem_by_sub(probs, nprob, sub);
+    const KmProb pr = probs[p];
+    for (int k = lane; k <= K; k += 32) cnt[k] = offs[(size_t)p * (K + 1) + k] + hist[(size_t)sub * (K + 1) + k];
+    __syncwarp();
+    const long long r0 = (long long)(sub - pr.sub0) * kSubTile;
+    const long long r1 = r0 + kSubTile < pr.rows ? r0 + kSubTile : pr.rows;
+    const int* lab = labels + pr.row0;
+    int* mem = member + pr.row0;
+    for (long long base = r0; base < r1; base += 32) {
+        const long long i = base + lane;
+        const bool act = i < r1;
+        int l = act ? lab[i] : -2 - lane;  // inactive lanes get unique dummy keys
+        int bin = act ? (l >= 0 && l < K ? l : K) : l;
+        unsigned peers = __match_any_sync(GSX_FULL, bin);
+        int rank = __popc(peers & ((1u << lane) - 1u));
+        int pos = 0;
+        if (act) pos = cnt[bin] + rank;
+        __syncwarp();
+        if (act && rank == 0) cnt[bin] += __popc(peers);
+        __syncwarp();
+        if (act) mem[pos] = (int)i;
+    }
+}
+
+// phase 5: one warp per (problem, cluster): serial index-order float32 sums over the member list
+__global__ void __launch_bounds__(256)
+    k_km_accum(const float* __restrict__ X, float* __restrict__ C, const int* __restrict__ member,
+               const int* __restrict__ offs, const int* __restrict__ counts, const KmProb* __restrict__ probs,
+               int nprob, int K, int D) {
+    const int lane = threadIdx.x & 31;
+    const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (wid >= (long long)nprob * K) return;
+    const int p = (int)(wid / K), c = (int)(wid - (long long)p * K);
+    const KmProb pr = probs[p];
+    const int cnt = counts[(size_t)p * K + c];
+    const int* mem = member + pr.row0 + offs[(size_t)p * (K + 1) + c];
+    const float* Xp = X + (size_t)pr.row0 * D;
+    float* out = C + ((size_t)p * K + c) * D;
+    const float inv = cnt > 0 ? __fdiv_rn(1.0f, (float)cnt) : 0.f;
+    for (int d0 = 0; d0 < D; d0 += 64) {
+        const int da = d0 + lane, db = d0 + 32 + lane;
+        const bool ha = da < D, hb = db < D;
+        float sa = 0.f, sb = 0.f;
+        for (int base = 0; base < cnt; base += 32) {
+            const int mine = base + lane < cnt ? __ldg(mem + base + lane) : 0;
+            const int nn = cnt - base < 32 ? cnt - base : 32;
+            int u = 0;
+            for (; u + 8 <= nn; u += 8) {  // 8 rows in flight, then 8 adds in index order
+                float va[8], vb[8];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    const float* xr = Xp + (size_t)__shfl_sync(GSX_FULL, mine, u + t) * D;
+                    va[t] = ha ? __ldg(xr + da) : 0.f;
+                    vb[t] = hb ? __ldg(xr + db) : 0.f;
+                }
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    sa = __fadd_rn(sa, va[t]);
+                    sb = __fadd_rn(sb, vb[t]);
+                }
+            }
+            for (; u < nn; ++u) {
+                const float* xr = Xp + (size_t)__shfl_sync(GSX_FULL, mine, u) * D;
+                if (ha) sa = __fadd_rn(sa, __ldg(xr + da));
+                if (hb) sb = __fadd_rn(sb, __ldg(xr + db));
+            }
+        }
+        if (cnt > 0) {
+            sa = __fmul_rn(sa, inv);
+            sb = __fmul_rn(sb, inv);
+        }
+        if (ha) out[da] = sa;
+        if (hb) out[db] = sb;
+    }
+}
+
+static long long total_subtiles(const int64_t* row_off, int nprob) {
+    long long t = 0;
+    for (int p = 0; p < nprob; ++p) t += (row_off[p + 1] - row_off[p] + kSubTile - 1) / kSubTile;
+    return t;
+}
+
+struct KmWs {
+    KmProb* probs;
+    int* member;
+    int* hist;
+    int* totals;
+    int* offs;
+    size_t total;
+    bool ok;
+};
+
+static KmWs km_carve(void* ws, size_t bytes, int64_t n_total, int nprob, int K, long long nsub) {
+    KmWs w;
+    Carver c(ws, bytes);
+    w.probs = c.take<KmProb>(nprob);
+    w.member = c.take<int>((size_t)n_total);
+    const bool sorted = K <= kMaxSortK;
+    w.hist = c.take<int>(sorted ? (size_t)nsub * (K + 1) : 1);
+    w.totals = c.take<int>(sorted ? (size_t)nprob * (K + 1) : 1);
+    w.offs = c.take<int>(sorted ? (size_t)nprob * (K + 1) : 1);
+    w.total = align_up(c.off, 256);
+    w.ok = c.ok();
+    return w;
+}
+
 int64_t kmeans_workspace_bytes(int64_t n_total, int nprob, int K, int D) {
-    (void)n_total;
-    (void)K;
     (void)D;
-    return (int64_t)align_up((size_t)(nprob > 0 ? nprob : 1) * sizeof(KmProb), 256) + 1024;
+    if (nprob < 1) nprob = 1;
+    if (n_total < 1) n_total = 1;
+    // worst case number of sub-tiles: every problem adds at most one partial tile
+    long long nsub = n_total / kSubTile + nprob + 1;
+    KmWs w = km_carve(nullptr, 0, n_total, nprob, K, nsub);
+    return (int64_t)w.total + 1024;
 }
 
 template <int D>
@@ -229,24 +448,38 @@ static int points_per_thread(int D) {
 int kmeans_lloyd(const float* X, const int64_t* row_off, int nprob, int K, int D, int max_iter, float* C, int* labels,
                  int* counts, void* ws, int64_t ws_bytes, cudaStream_t st) {
     GSX_REQUIRE(nprob >= 1 && K >= 1 && D >= 1 && max_iter >= 0, GSX_ERR_ARG, "kmeans: bad shape");
-    GSX_REQUIRE(ws_bytes >= kmeans_workspace_bytes(row_off[nprob] - row_off[0], nprob, K, D), GSX_ERR_WORKSPACE,
+    const int64_t n_total = row_off[nprob] - row_off[0];
+    GSX_REQUIRE(row_off[0] == 0, GSX_ERR_ARG, "kmeans: row_off[0] must be 0");
+    GSX_REQUIRE(ws_bytes >= kmeans_workspace_bytes(n_total, nprob, K, D), GSX_ERR_WORKSPACE,
                 "kmeans: workspace too small");
     const int per_tile = kAssignThreads * points_per_thread(D);
     std::vector<KmProb> hp(nprob);
-    long long tiles = 0;
+    long long tiles = 0, nsub = 0;
     for (int p = 0; p < nprob; ++p) {
         hp[p].row0 = row_off[p];
         hp[p].rows = row_off[p + 1] - row_off[p];
         GSX_REQUIRE(hp[p].rows >= 1, GSX_ERR_ARG, "kmeans: empty problem %d", p);
+        GSX_REQUIRE(hp[p].rows < 2147483647ll, GSX_ERR_UNSUPPORTED, "kmeans: problem %d has too many rows", p);
         hp[p].tile0 = (int)tiles;
+        hp[p].sub0 = (int)nsub;
         tiles += (hp[p].rows + per_tile - 1) / per_tile;
+        nsub += (hp[p].rows + kSubTile - 1) / kSubTile;
     }
     GSX_REQUIRE(tiles < 2147483647ll, GSX_ERR_UNSUPPORTED, "kmeans: too many tiles");
-    KmProb* dp = (KmProb*)ws;
+    GSX_REQUIRE(nsub == total_subtiles(row_off, nprob), GSX_ERR_ARG, "kmeans: internal tile count mismatch");
+    KmWs w = km_carve(ws, (size_t)ws_bytes, n_total, nprob, K, nsub);
+    GSX_REQUIRE(w.ok, GSX_ERR_WORKSPACE, "kmeans: workspace too small");
+    KmProb* dp = w.probs;
     GSX_CUDA_CHECK(cudaMemcpyAsync(dp, hp.data(), hp.size() * sizeof(KmProb), cudaMemcpyHostToDevice, st));
     GSX_CUDA_CHECK(cudaStreamSynchronize(st));  // hp is a local pageable buffer
     const long long uwarps = (long long)nprob * K;
     const int ublocks = (int)((uwarps * 32 + 255) / 256);
+    const bool sorted = K <= kMaxSortK;
+    const size_t smem = (size_t)8 * (K + 1) * sizeof(int);
+    if (sorted && smem > 48 * 1024) {
+        GSX_CUDA_CHECK(cudaFuncSetAttribute(k_km_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GSX_CUDA_CHECK(cudaFuncSetAttribute(k_km_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
     for (int it = 0; it < max_iter; ++it) {
         switch (D) {
             case 1: launch_assign<1>(X, C, labels, dp, nprob, K, (int)tiles, st); break;
@@ -260,7 +493,21 @@ int kmeans_lloyd(const float* X, const int64_t* row_off, int nprob, int K, int D
                 k_kmeans_assign_generic<<<(int)tiles, kAssignThreads, 0, st>>>(X, C, labels, dp, nprob, K, D);
         }
         GSX_KERNEL_CHECK();
-        k_kmeans_update<<<ublocks, 256, 0, st>>>(X, C, labels, counts, dp, nprob, K, D);
+        if (!sorted) {  // very large K: O(N*K/32) label scan per cluster (no shared-memory counters needed)
+            k_kmeans_update<<<ublocks, 256, 0, st>>>(X, C, labels, counts, dp, nprob, K, D);
+            GSX_KERNEL_CHECK();
+            continue;
+        }
+        const int sblocks = (int)((nsub + 7) / 8);
+        k_km_hist<<<sblocks, 256, smem, st>>>(labels, dp, nprob, K, (int)nsub, w.hist);
+        GSX_KERNEL_CHECK();
+        k_km_scan<<<dim3((K + 1 + 255) / 256, nprob), 256, 0, st>>>(dp, nprob, K, (int)nsub, w.hist, w.totals);
+        GSX_KERNEL_CHECK();
+        k_km_offsets<<<nprob, 256, 0, st>>>(nprob, K, w.totals, w.offs, counts);
+        GSX_KERNEL_CHECK();
+        k_km_scatter<<<sblocks, 256, smem, st>>>(labels, dp, nprob, K, (int)nsub, w.hist, w.offs, w.member);
+        GSX_KERNEL_CHECK();
+        k_km_accum<<<ublocks, 256, 0, st>>>(X, C, w.member, w.offs, counts, dp, nprob, K, D);
         GSX_KERNEL_CHECK();
     }
     return GSX_OK;

@@ -14,7 +14,8 @@ def _kmeans_data(n, d):
 
 
 @pytest.mark.parametrize("n,d,k,it", [(20_000, 45, 64, 5), (50_000, 1, 256, 20), (10_000, 9, 16, 10),
-                                      (10_000, 24, 100, 3), (3_000, 3, 7, 4), (5_000, 5, 33, 3), (4_000, 45, 300, 2)])
+                                      (10_000, 24, 100, 3), (3_000, 3, 7, 4), (5_000, 5, 33, 3), (4_000, 45, 300, 2), (6_000, 3, 2100, 2),
+                                      (300_000, 45, 256, 2), (2_500, 9, 1024, 3)])
 def test_kmeans_matches_oracle(n, d, k, it, cuda, gsx_lib):
     import torch
     import oracle
