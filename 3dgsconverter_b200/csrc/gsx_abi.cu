@@ -7,6 +7,7 @@
 #include "gsx_common.cuh"
 #include "gsx_density.cuh"
 #include "gsx_kmeans.cuh"
+#include "gsx_knn_exact.cuh"
 #include "gsx_masks.cuh"
 #include "gsx_sor.cuh"
 
@@ -195,6 +196,40 @@ int gsx_sor_filter_host(const float* xyz_host, int64_t n, int32_t k, float thres
     GSX_CUDA_CHECK(cudaMemcpyAsync(xyz.p, xyz_host, (size_t)n * 12, cudaMemcpyHostToDevice, st));
     if ((rc = gsx_sor_filter_device((const float*)xyz.p, n, k, threshold_factor, hash_mode, (uint8_t*)mask.p,
                                     (float*)means.p, ws.p, wsb, st)))
+        return rc;
+    GSX_CUDA_CHECK(cudaMemcpyAsync(mask_host, mask.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+    if (means_host) GSX_CUDA_CHECK(cudaMemcpyAsync(means_host, means.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    GSX_CUDA_CHECK(cudaStreamSynchronize(st));
+    return GSX_OK;
+}
+
+/* ------------------------------------------------------------------ SOR, cKDTree semantics */
+
+int64_t gsx_knn_exact_workspace_bytes(int64_t n) { return knn_exact_workspace_bytes(n); }
+
+int gsx_knn_exact_mean_dists(const float* xyz_dev, int64_t n, int32_t k, float* means_dev, void* ws, int64_t ws_bytes,
+                             void* stream) {
+    return knn_exact_mean_dists(xyz_dev, n, k, means_dev, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int gsx_sor_ckdtree_filter_host(const float* xyz_host, int64_t n, int32_t k, float threshold_factor, uint8_t* mask_host,
+                                float* means_host) {
+    GSX_REQUIRE(n >= 1 && n < 2147483584ll, GSX_ERR_ARG, "sor: n=%lld out of range", (long long)n);
+    cudaStream_t st = 0;
+    int64_t wsb = knn_exact_workspace_bytes(n);
+    int64_t msb = (int64_t)mean_std_ws_bytes(n);
+    DevBuf xyz(st), ws(st), mask(st), means(st), ms(st), msws(st);
+    int rc;
+    if ((rc = xyz.alloc((size_t)n * 12))) return rc;
+    if ((rc = ws.alloc((size_t)wsb))) return rc;
+    if ((rc = mask.alloc((size_t)n))) return rc;
+    if ((rc = means.alloc((size_t)n * 4))) return rc;
+    if ((rc = ms.alloc(64))) return rc;
+    if ((rc = msws.alloc((size_t)msb))) return rc;
+    GSX_CUDA_CHECK(cudaMemcpyAsync(xyz.p, xyz_host, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+    if ((rc = knn_exact_mean_dists((const float*)xyz.p, n, k, (float*)means.p, ws.p, wsb, st))) return rc;
+    if ((rc = mean_std_f32((const float*)means.p, n, (float*)ms.p, msws.p, (size_t)msb, st))) return rc;
+    if ((rc = threshold_mask((const float*)means.p, n, (const float*)ms.p, threshold_factor, (uint8_t*)mask.p, st)))
         return rc;
     GSX_CUDA_CHECK(cudaMemcpyAsync(mask_host, mask.p, (size_t)n, cudaMemcpyDeviceToHost, st));
     if (means_host) GSX_CUDA_CHECK(cudaMemcpyAsync(means_host, means.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));

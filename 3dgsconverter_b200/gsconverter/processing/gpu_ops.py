@@ -68,4 +68,7 @@ def filter_sor_gpu(data_np: np.ndarray, k: int = 25, threshold_factor: float = 1
     if d != 3:
         raise ValueError("Requires 3D data")
     from gsx import sor as _sor
+    if os.environ.get("GSX_SOR_SEMANTICS", "taichi") == "ckdtree":
+        # opt-in: the arithmetic of the reference's CPU path (data_processor.py:155-180, exact float64 KNN)
+        return _sor.ckdtree_filter_host(data_np, int(k), float(threshold_factor))
     return _sor.sor_filter_host(data_np, int(k), float(threshold_factor), hash_mode=_hash_mode())

@@ -45,6 +45,9 @@ _SIGS = {
     "gsx_threshold_mask": (C.c_int, [_vp, _i64, _vp, C.c_float, _vp, _vp]),
     "gsx_sor_filter_device": (C.c_int, [_vp, _i64, _i32, C.c_float, _i32, _vp, _vp, _vp, _i64, _vp]),
     "gsx_sor_filter_host": (C.c_int, [_vp, _i64, _i32, C.c_float, _i32, _vp, _vp]),
+    "gsx_knn_exact_workspace_bytes": (_i64, [_i64]),
+    "gsx_knn_exact_mean_dists": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _i64, _vp]),
+    "gsx_sor_ckdtree_filter_host": (C.c_int, [_vp, _i64, _i32, C.c_float, _vp, _vp]),
     "gsx_bbox_mask": (C.c_int, [_vp, _i64, _f32p, _vp, _vp]),
     "gsx_alpha_mask": (C.c_int, [_vp, _i64, C.c_double, _vp, _vp]),
     "gsx_alpha_logit_threshold": (C.c_double, [C.c_double]),

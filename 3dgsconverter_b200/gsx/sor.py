@@ -133,3 +133,36 @@ def sor_filter_host(data_np: np.ndarray, k: int = 25, threshold_factor: float = 
                                   mask.ctypes.data_as(C.c_void_p),
                                   means.ctypes.data_as(C.c_void_p) if return_means else None), "gsx_sor_filter_host")
     return (mask, means) if return_means else mask
+
+
+# ------------------------------------------------------------------ cKDTree semantics (the reference's CPU path)
+def ckdtree_mean_dists(xyz: torch.Tensor, k: int) -> torch.Tensor:
+    """data_processor.py:160-173 on device: exact (k+1)-NN in float64, mean of neighbours 1..k -> float32."""
+    _check_xyz(xyz)
+    n = xyz.shape[0]
+    ws = torch.empty(lib.gsx_knn_exact_workspace_bytes(n), dtype=torch.uint8, device=xyz.device)
+    out = torch.empty(n, dtype=torch.float32, device=xyz.device)
+    check(lib.gsx_knn_exact_mean_dists(_ptr(xyz), n, int(k), _ptr(out), _ptr(ws), ws.numel(), _stream()),
+          "gsx_knn_exact_mean_dists")
+    return out
+
+
+def ckdtree_filter(xyz: torch.Tensor, k: int = 25, threshold_factor: float = 10.5, return_means: bool = False):
+    """data_processor.py:155-180 on device: the mask the reference computes (and then discards)."""
+    means = ckdtree_mean_dists(xyz, k)
+    mask = threshold_mask(means, mean_std(means), threshold_factor)
+    return (mask, means) if return_means else mask
+
+
+def ckdtree_filter_host(data_np: np.ndarray, k: int = 25, threshold_factor: float = 10.5, return_means: bool = False):
+    if data_np.ndim != 2 or data_np.shape[1] != 3:
+        raise ValueError("Requires 3D data")
+    pos = np.ascontiguousarray(data_np, dtype=np.float32)
+    n = pos.shape[0]
+    mask = np.empty(n, dtype=np.bool_)
+    means = np.empty(n, dtype=np.float32) if return_means else None
+    check(lib.gsx_sor_ckdtree_filter_host(pos.ctypes.data_as(C.c_void_p), n, int(k), float(np.float32(threshold_factor)),
+                                          mask.ctypes.data_as(C.c_void_p),
+                                          means.ctypes.data_as(C.c_void_p) if return_means else None),
+          "gsx_sor_ckdtree_filter_host")
+    return (mask, means) if return_means else mask

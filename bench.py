@@ -271,7 +271,7 @@ def main():
                         "lower); the reference's un-pruned gather model (16 B x V visits) would read "
                         "reference_gather_model_GBps"}
     prof = ROOT / "profiles" / "r01_knn_traffic.json"
-    if prof.exists():
+    if prof.exists() and world == 1 and n == 10_000_000 and args.kind == "mixed" and args.hash == "i32wrap":
         try:
             roofline["traffic"] = json.loads(prof.read_text()).get("dram_bytes_per_launch")
         except Exception:

@@ -90,6 +90,18 @@ int gsx_sor_filter_device(const float* xyz_dev, int64_t n, int32_t k, float thre
 int gsx_sor_filter_host(const float* xyz_host, int64_t n, int32_t k, float threshold_factor, int32_t hash_mode,
                         uint8_t* mask_host, float* means_host);
 
+/* ---- SOR, cKDTree semantics: data_processor.py:155-180 (the reference's CPU path) ------------ */
+/* data_processor.py:160-173: exact (k+1)-NN in float64 over the float32 coordinates (the nearest is the
+ * point itself or a coincident twin and is dropped), mean of neighbours 1..k in float64 (NumPy pairwise
+ * row reduction), stored as float32 in the caller's point order.  1 <= k <= 63. */
+int64_t gsx_knn_exact_workspace_bytes(int64_t n);
+int gsx_knn_exact_mean_dists(const float* xyz_dev, int64_t n, int32_t k, float* means_dev, void* ws, int64_t ws_bytes,
+                             void* stream);
+/* the same plus data_processor.py:176-180 (threshold and mask -- the mask the reference computes and then
+ * discards) on HOST buffers. */
+int gsx_sor_ckdtree_filter_host(const float* xyz_host, int64_t n, int32_t k, float threshold_factor, uint8_t* mask_host,
+                                float* means_host);
+
 /* ---- bbox / alpha masks: data_processor.py:215-231, :184-213 ------------------------ */
 /* keep <=> lo <= v <= hi on all axes, float32 compares (bounds already rounded to float32 by caller). */
 int gsx_bbox_mask(const float* xyz_dev, int64_t n, const float* lohi_host /*[6]*/, uint8_t* mask_dev, void* stream);
