@@ -273,6 +273,22 @@ int gsx_density_member_mask(const float* xyz_dev, int64_t n, float voxel, const 
                                (cudaStream_t)stream);
 }
 
+void gsx_density_voxel_range(const float* minmax_host, float voxel, int64_t* q0_out, int64_t* dim_out) {
+    density_voxel_range(minmax_host, voxel, q0_out, dim_out);
+}
+
+int gsx_density_grid_count(const float* xyz_dev, int64_t n, float voxel, const int64_t* q0, const int64_t* dim,
+                           int32_t* grid_dev, unsigned long long* oob_dev, void* stream) {
+    return density_grid_count(xyz_dev, n, voxel, q0, dim, grid_dev, oob_dev, (cudaStream_t)stream);
+}
+
+int gsx_density_grid_dense(const int32_t* grid_dev, const int64_t* q0, const int64_t* dim, int64_t min_points,
+                           int64_t* dense_vox_host, int32_t* dense_cnt_host, int64_t cap, int64_t* n_dense_host,
+                           int64_t* n_voxels_host, void* ws, int64_t ws_bytes, void* stream) {
+    return density_grid_dense(grid_dev, q0, dim, min_points, dense_vox_host, dense_cnt_host, cap, n_dense_host,
+                              n_voxels_host, ws, ws_bytes, (cudaStream_t)stream);
+}
+
 /* ------------------------------------------------------------------ K-Means */
 
 int64_t gsx_kmeans_workspace_bytes(int64_t n_total, int32_t nprob, int32_t K, int32_t D) {

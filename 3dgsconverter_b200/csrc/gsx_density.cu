@@ -218,6 +218,112 @@ int density_voxel_count(const float* xyz, int64_t n, float voxel, int64_t min_po
     return GSX_OK;
 }
 
+// ---------------------------------------------------------------- staged dense-grid API (multi-GPU)
+// Rank-local histogram into a caller-owned int32 grid over a caller-chosen voxel box (the global one);
+// the caller all-reduces the grid and then extracts the dense voxels.
+__global__ void __launch_bounds__(256) k_vox_count_grid_only(const float* __restrict__ xyz, int64_t n, float voxel,
+                                                             VoxGrid g, int* __restrict__ grid,
+                                                             unsigned long long* __restrict__ oob) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long rx = voxel_of(xyz[3 * i], voxel) - g.q0[0], ry = voxel_of(xyz[3 * i + 1], voxel) - g.q0[1],
+              rz = voxel_of(xyz[3 * i + 2], voxel) - g.q0[2];
+    if (rx < 0 || ry < 0 || rz < 0 || rx >= g.dim[0] || ry >= g.dim[1] || rz >= g.dim[2]) {
+        atomicAdd(oob, 1ull);
+        return;
+    }
+    atomicAdd(grid + ((size_t)rx * g.dim[1] + (size_t)ry) * g.dim[2] + (size_t)rz, 1);
+}
+
+__global__ void __launch_bounds__(256) k_vox_grid_dense(const int* __restrict__ grid, size_t ncell, VoxGrid g, int thr,
+                                                        unsigned long long* __restrict__ counters,
+                                                        long long* __restrict__ dense_vox,
+                                                        int* __restrict__ dense_cnt, int64_t cap) {
+    size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= ncell) return;
+    int v = grid[c];
+    if (v > 0) atomicAdd(counters + 1, 1ull);
+    if (v >= thr) {
+        unsigned long long slot = atomicAdd(counters, 1ull);
+        if ((int64_t)slot < cap) {
+            long long z = (long long)(c % (size_t)g.dim[2]);
+            long long y = (long long)((c / (size_t)g.dim[2]) % (size_t)g.dim[1]);
+            long long x = (long long)(c / ((size_t)g.dim[2] * (size_t)g.dim[1]));
+            dense_vox[3 * slot] = x + g.q0[0];
+            dense_vox[3 * slot + 1] = y + g.q0[1];
+            dense_vox[3 * slot + 2] = z + g.q0[2];
+            dense_cnt[slot] = v;
+        }
+    }
+}
+
+static int make_grid(const int64_t* q0, const int64_t* dim, VoxGrid& g, size_t& ncell) {
+    double cells = 1.0;
+    for (int a = 0; a < 3; ++a) {
+        g.q0[a] = q0[a];
+        g.dim[a] = dim[a];
+        GSX_REQUIRE(dim[a] >= 1 && dim[a] < kAxisLim, GSX_ERR_ARG, "density: bad grid extent on axis %d", a);
+        cells *= (double)dim[a];
+    }
+    GSX_REQUIRE(cells < 4.0e9, GSX_ERR_UNSUPPORTED, "density: grid too large for the dense path");
+    ncell = (size_t)dim[0] * dim[1] * dim[2];
+    return GSX_OK;
+}
+
+void density_voxel_range(const float* minmax_host, float voxel, int64_t* q0, int64_t* dim) {
+    for (int a = 0; a < 3; ++a) {
+        q0[a] = voxel_of(minmax_host[a], voxel);
+        dim[a] = voxel_of(minmax_host[3 + a], voxel) - q0[a] + 1;
+    }
+}
+
+int density_grid_count(const float* xyz, int64_t n, float voxel, const int64_t* q0, const int64_t* dim, int* grid_dev,
+                       unsigned long long* oob_dev, cudaStream_t st) {
+    if (n == 0) return GSX_OK;
+    GSX_REQUIRE(voxel > 0.f, GSX_ERR_ARG, "density: voxel size must be > 0");
+    VoxGrid g;
+    size_t ncell;
+    int rc = make_grid(q0, dim, g, ncell);
+    if (rc) return rc;
+    k_vox_count_grid_only<<<(int)((n + 255) / 256), 256, 0, st>>>(xyz, n, voxel, g, grid_dev, oob_dev);
+    GSX_KERNEL_CHECK();
+    return GSX_OK;
+}
+
+int density_grid_dense(const int* grid_dev, const int64_t* q0, const int64_t* dim, int64_t min_points,
+                       int64_t* dense_vox_host, int32_t* dense_cnt_host, int64_t cap, int64_t* n_dense_host,
+                       int64_t* n_voxels_host, void* ws, int64_t ws_bytes, cudaStream_t st) {
+    VoxGrid g;
+    size_t ncell;
+    int rc = make_grid(q0, dim, g, ncell);
+    if (rc) return rc;
+    GSX_REQUIRE(cap >= 1, GSX_ERR_ARG, "density: cap must be >= 1");
+    Carver c(ws, (size_t)ws_bytes);
+    unsigned long long* counters = c.take<unsigned long long>(4);
+    long long* dvox = c.take<long long>(3 * (size_t)cap);
+    int* dcnt = c.take<int>((size_t)cap);
+    GSX_REQUIRE(c.ok(), GSX_ERR_WORKSPACE, "density: workspace too small for cap=%lld", (long long)cap);
+    long long thr_ll = min_points < 1 ? 1 : min_points;
+    GSX_REQUIRE(thr_ll < 2147483647ll, GSX_ERR_ARG, "density: min_points too large");
+    GSX_CUDA_CHECK(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned long long), st));
+    k_vox_grid_dense<<<(unsigned)((ncell + 255) / 256), 256, 0, st>>>(grid_dev, ncell, g, (int)thr_ll, counters, dvox,
+                                                                      dcnt, cap);
+    GSX_KERNEL_CHECK();
+    unsigned long long hc[2];
+    GSX_CUDA_CHECK(cudaMemcpyAsync(hc, counters, sizeof(hc), cudaMemcpyDeviceToHost, st));
+    GSX_CUDA_CHECK(cudaStreamSynchronize(st));
+    *n_dense_host = (int64_t)hc[0];
+    if (n_voxels_host) *n_voxels_host = (int64_t)hc[1];
+    GSX_REQUIRE((int64_t)hc[0] <= cap, GSX_ERR_WORKSPACE, "density: %llu dense voxels exceed cap %lld", hc[0],
+                (long long)cap);
+    if (hc[0] > 0) {
+        GSX_CUDA_CHECK(cudaMemcpyAsync(dense_vox_host, dvox, (size_t)hc[0] * 24, cudaMemcpyDeviceToHost, st));
+        GSX_CUDA_CHECK(cudaMemcpyAsync(dense_cnt_host, dcnt, (size_t)hc[0] * 4, cudaMemcpyDeviceToHost, st));
+        GSX_CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    return GSX_OK;
+}
+
 // ---------------------------------------------------------------- membership mask
 __global__ void __launch_bounds__(256) k_vox_member(const float* __restrict__ xyz, int64_t n, float voxel,
                                                     long long ox, long long oy, long long oz,

@@ -110,3 +110,45 @@ def density_filter(xyz: torch.Tensor, voxel_size=1.0, threshold_percentage=0.32,
     keep, n_kept, max_len = select_clusters(vox, keep_multicluster)
     mask = member_mask(xyz, voxel_size, keep, ws)
     return mask, dict(clusters=n_kept, max_len=max_len, dense=len(vox), voxels=n_unique)
+
+
+# ------------------------------------------------------------------ staged / sharded form
+GRID_CELL_LIMIT = 1 << 28   # 1 GiB of int32 counters
+
+
+def voxel_range(minmax: np.ndarray, voxel_size: float):
+    """Voxel-space origin and extent of a bounding box (floor(x / f32(voxel)) is monotone)."""
+    mm = np.ascontiguousarray(minmax, dtype=np.float32)
+    q0 = (C.c_int64 * 3)()
+    dim = (C.c_int64 * 3)()
+    lib.gsx_density_voxel_range(mm.ctypes.data_as(C.POINTER(C.c_float)), float(np.float32(voxel_size)), q0, dim)
+    return np.array(q0[:], dtype=np.int64), np.array(dim[:], dtype=np.int64)
+
+
+def grid_count(xyz: torch.Tensor, voxel_size: float, q0: np.ndarray, dim: np.ndarray, grid: torch.Tensor):
+    """Accumulate this slab's voxel histogram into `grid` (int32, prod(dim) cells, caller-zeroed)."""
+    _check_xyz(xyz)
+    oob = torch.zeros(1, dtype=torch.int64, device=xyz.device)
+    q0c = (C.c_int64 * 3)(*[int(v) for v in q0])
+    dimc = (C.c_int64 * 3)(*[int(v) for v in dim])
+    check(lib.gsx_density_grid_count(_ptr(xyz), xyz.shape[0], float(np.float32(voxel_size)), q0c, dimc, _ptr(grid),
+                                     _ptr(oob), _stream()), "gsx_density_grid_count")
+    return oob
+
+
+def grid_dense(grid: torch.Tensor, q0: np.ndarray, dim: np.ndarray, min_points: int, n_total: int):
+    """Dense voxels (count >= max(min_points,1)) of an (all-reduced) grid, lexicographically sorted."""
+    thr = max(int(min_points), 1)
+    cap = n_total // thr + 1
+    ws = torch.empty(cap * 28 + 4096, dtype=torch.uint8, device=grid.device)
+    vox = np.empty((cap, 3), dtype=np.int64)
+    cnt = np.empty(cap, dtype=np.int32)
+    nd, nv = C.c_int64(0), C.c_int64(0)
+    q0c = (C.c_int64 * 3)(*[int(v) for v in q0])
+    dimc = (C.c_int64 * 3)(*[int(v) for v in dim])
+    check(lib.gsx_density_grid_dense(_ptr(grid), q0c, dimc, int(min_points), vox.ctypes.data_as(C.c_void_p),
+                                     cnt.ctypes.data_as(C.c_void_p), cap, C.byref(nd), C.byref(nv), _ptr(ws),
+                                     ws.numel(), _stream()), "gsx_density_grid_dense")
+    vox, cnt = vox[: nd.value], cnt[: nd.value]
+    order = np.lexsort((vox[:, 2], vox[:, 1], vox[:, 0]))
+    return vox[order], cnt[order], nv.value

@@ -92,3 +92,63 @@ def kmeans_chunks_sharded(X_chunks, K: int, max_iter: int, inits, group=None, ru
         if p % world == rank:
             out[p] = runner(X_chunks[p], K, max_iter, inits[p])
     return out
+
+
+class _GsxDensityOps:
+    """Device ops of the sharded density filter (replaceable in CPU/gloo tests)."""
+
+    def minmax(self, xyz):
+        return torch.cat([xyz.min(dim=0).values, xyz.max(dim=0).values])
+
+    def voxel_range(self, mm, voxel):
+        from . import density
+        return density.voxel_range(mm, voxel)
+
+    def grid_count(self, xyz, voxel, q0, dim, grid):
+        from . import density
+        density.grid_count(xyz, voxel, q0, dim, grid)
+
+    def grid_dense(self, grid, q0, dim, min_points, n_total):
+        from . import density
+        return density.grid_dense(grid, q0, dim, min_points, n_total)
+
+    def member_mask(self, xyz, voxel, keep):
+        from . import density
+        return density.member_mask(xyz, voxel, keep)
+
+
+def density_filter_sharded(xyz_local: torch.Tensor, voxel_size=1.0, threshold_percentage=0.32, sensitivity=None,
+                           keep_multicluster=False, group=None, ops=None):
+    """Density keep-mask of this rank's slab, identical to the single-GPU filter on the union cloud.
+    all-reduce(min/max) of 6 floats -> global voxel box -> rank-local int32 histogram -> ONE all-reduce(sum)
+    of the grid -> identical (tiny) host cluster selection on every rank -> local membership mask."""
+    from . import density
+    ops = ops or _GsxDensityOps()
+    if sensitivity is not None:
+        voxel_size, threshold_percentage = density.slider(sensitivity)
+    n_local = torch.tensor([xyz_local.shape[0]], dtype=torch.int64, device=xyz_local.device)
+    dist.all_reduce(n_local, group=group)
+    n_total = int(n_local.item())
+    mm = ops.minmax(xyz_local)
+    lo, hi = mm[:3].clone(), mm[3:].clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    q0, dim = ops.voxel_range(torch.cat([lo, hi]).cpu().numpy(), voxel_size)
+    ncell = int(dim[0]) * int(dim[1]) * int(dim[2])
+    if ncell > density.GRID_CELL_LIMIT:
+        # sparse far-flung cloud: replicate (all-gather) and run the single-GPU hash-table path on every rank
+        xyz_all, sizes = _all_gather_rows(xyz_local, group)
+        mask_all, info = density.density_filter(xyz_all, voxel_size, threshold_percentage, None, keep_multicluster)
+        off = sum(sizes[: dist.get_rank(group)])
+        return mask_all[off: off + xyz_local.shape[0]], info
+    grid = torch.zeros(ncell, dtype=torch.int32, device=xyz_local.device)
+    ops.grid_count(xyz_local, voxel_size, q0, dim, grid)
+    dist.all_reduce(grid, op=dist.ReduceOp.SUM, group=group)
+    min_points = int(n_total * (threshold_percentage / 100.0))  # data_processor.py:48 on the global count
+    vox, cnt, n_unique = ops.grid_dense(grid, q0, dim, min_points, n_total)
+    if len(vox) == 0:
+        return torch.zeros(xyz_local.shape[0], dtype=torch.bool, device=xyz_local.device), dict(
+            clusters=0, max_len=0, dense=0, voxels=n_unique)
+    keep, n_kept, max_len = density.select_clusters(vox, keep_multicluster)
+    mask = ops.member_mask(xyz_local, voxel_size, keep)
+    return mask, dict(clusters=n_kept, max_len=max_len, dense=len(vox), voxels=n_unique)

@@ -125,6 +125,17 @@ int gsx_density_voxel_count(const float* xyz_dev, int64_t n, float voxel, int64_
 int gsx_density_member_mask(const float* xyz_dev, int64_t n, float voxel, const int64_t* keep_vox_host, int64_t n_keep,
                             uint8_t* mask_dev, void* ws, int64_t ws_bytes, void* stream);
 
+/* Staged form for sharded clouds (one process per GPU): every rank counts its slab into an int32 grid over
+ * the GLOBAL voxel box (q0[3], dim[3] voxels; from the all-reduced min/max via gsx_density_voxel_range), the
+ * caller all-reduces the grid (sum) and extracts the dense voxels from it.  Same results as
+ * gsx_density_voxel_count on the union cloud.  *oob_dev counts points outside the box (must stay 0). */
+void gsx_density_voxel_range(const float* minmax_host /*[6]*/, float voxel, int64_t* q0_out, int64_t* dim_out);
+int gsx_density_grid_count(const float* xyz_dev, int64_t n, float voxel, const int64_t* q0, const int64_t* dim,
+                           int32_t* grid_dev, unsigned long long* oob_dev, void* stream);
+int gsx_density_grid_dense(const int32_t* grid_dev, const int64_t* q0, const int64_t* dim, int64_t min_points,
+                           int64_t* dense_vox_host, int32_t* dense_cnt_host, int64_t cap, int64_t* n_dense_host,
+                           int64_t* n_voxels_host, void* ws, int64_t ws_bytes, void* stream);
+
 /* ---- K-Means: gpu_ops.py:57-96 (kernels) + :186-188 (Lloyd loop) ---------------------- */
 /* Batched over `nprob` independent problems stored back to back (SOG shN chunks, sog.py:527-549):
  * problem p has rows [row_off[p], row_off[p+1]) of X[*,D] and K centroids at C[p*K*D].

@@ -91,3 +91,75 @@ def test_query_range_partition():
             edges = [query_range(n, r, w) for r in range(w)]
             assert edges[0][0] == 0 and edges[-1][1] == n
             assert all(edges[i][1] == edges[i + 1][0] for i in range(w - 1))
+
+
+class OracleDensityOps:
+    """NumPy stand-in for the CUDA density ops (collective logic under test, CPU/gloo)."""
+
+    def minmax(self, xyz):
+        return torch.cat([xyz.min(dim=0).values, xyz.max(dim=0).values])
+
+    def voxel_range(self, mm, voxel):
+        v = np.float32(voxel)
+        q0 = np.floor(mm[:3].astype(np.float32) / v).astype(np.int64)
+        q1 = np.floor(mm[3:].astype(np.float32) / v).astype(np.int64)
+        return q0, q1 - q0 + 1
+
+    def grid_count(self, xyz, voxel, q0, dim, grid):
+        q = np.floor(xyz.numpy() / np.float32(voxel)).astype(np.int64) - q0
+        flat = (q[:, 0] * dim[1] + q[:, 1]) * dim[2] + q[:, 2]
+        grid += torch.from_numpy(np.bincount(flat, minlength=grid.numel()).astype(np.int32))
+
+    def grid_dense(self, grid, q0, dim, min_points, n_total):
+        g = grid.numpy().reshape(tuple(int(d) for d in dim))
+        idx = np.argwhere(g >= max(min_points, 1))
+        return idx + q0, g[tuple(idx.T)], int((g > 0).sum())
+
+    def member_mask(self, xyz, voxel, keep):
+        q = np.floor(xyz.numpy() / np.float32(voxel)).astype(np.int64)
+        ks = set(map(tuple, keep))
+        return torch.from_numpy(np.array([tuple(v) in ks for v in q]))
+
+
+def _density_worker(rank, world, port, sizes, q):
+    sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "3dgsconverter_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gsx import dist as gd, synth
+    xyz = synth.xyz(sum(sizes), "mixed")
+    off = sum(sizes[:rank])
+    local = torch.from_numpy(xyz[off:off + sizes[rank]].copy())
+    out = {}
+    for sens, multi in ((0.5, True), (0.9, False)):
+        mask, info = gd.density_filter_sharded(local, sensitivity=sens, keep_multicluster=multi,
+                                               ops=OracleDensityOps())
+        out[(sens, multi)] = (mask.numpy(), info)
+    q.put((rank, out))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_density_sharded_equals_single():
+    import oracle
+    from gsx import synth
+    sizes = (30_000, 20_000)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_density_worker, args=(r, 2, port, sizes, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(2):
+        r, out = q.get(timeout=300)
+        res[r] = out
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    xyz = synth.xyz(sum(sizes), "mixed")
+    for key in res[0]:
+        want, info = oracle.density_mask(xyz, sensitivity=key[0], keep_multicluster=key[1])
+        got = np.concatenate([res[0][key][0], res[1][key][0]])
+        assert np.array_equal(got, want), key
+        assert res[0][key][1]["clusters"] == info["clusters"] == res[1][key][1]["clusters"]

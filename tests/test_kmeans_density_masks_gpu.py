@@ -102,3 +102,23 @@ def test_bbox_alpha_match_oracle(cuda, gsx_lib):
         o = torch.from_numpy(op).to(cuda)
         for m in (1, 5, 128, 254):
             assert np.array_equal(masks.alpha_mask(o, m).cpu().numpy(), oracle.alpha_mask(op, m))
+
+
+def test_density_staged_grid_equals_one_shot(cuda, gsx_lib):
+    """The staged API used by the sharded driver (count into a caller grid, extract dense voxels)."""
+    import torch
+    from gsx import density, synth
+    xyz = synth.xyz(300_000, "mixed")
+    x = torch.from_numpy(xyz).to(cuda)
+    voxel, thr = density.slider(0.5)
+    mm = torch.cat([x.min(0).values, x.max(0).values]).cpu().numpy()
+    q0, dim = density.voxel_range(mm, voxel)
+    grid = torch.zeros(int(np.prod(dim)), dtype=torch.int32, device=cuda)
+    half = len(xyz) // 2
+    for part in (x[:half].contiguous(), x[half:].contiguous()):   # two "ranks" into one grid == all-reduce(sum)
+        oob = density.grid_count(part, voxel, q0, dim, grid)
+        assert int(oob.item()) == 0
+    mp_ = int(len(xyz) * (thr / 100.0))
+    vox, cnt, nuniq = density.grid_dense(grid, q0, dim, mp_, len(xyz))
+    vox2, cnt2, nuniq2, _ = density.dense_voxels(x, voxel, mp_)
+    assert np.array_equal(vox, vox2) and np.array_equal(cnt, cnt2) and nuniq == nuniq2
