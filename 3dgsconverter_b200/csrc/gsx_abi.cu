@@ -44,10 +44,24 @@ int sm_count() {
     return cached;
 }
 
+// keep freed blocks in the default memory pool across calls: without this the pool is trimmed at every
+// stream synchronisation and each *_host call pays ~20 ms of cudaMalloc for its workspace again
+static void keep_pool_warm() {
+    static thread_local int done_for = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    done_for = dev;
+}
+
 struct DevBuf {  // stream-ordered device allocation for the *_host entry points
     void* p = nullptr;
     cudaStream_t st;
-    explicit DevBuf(cudaStream_t s) : st(s) {}
+    explicit DevBuf(cudaStream_t s) : st(s) { keep_pool_warm(); }
     int alloc(size_t bytes) {
         cudaError_t e = cudaMallocAsync(&p, bytes ? bytes : 1, st);
         if (e != cudaSuccess) {
