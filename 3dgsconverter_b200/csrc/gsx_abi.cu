@@ -9,6 +9,7 @@
 #include "gsx_kmeans.cuh"
 #include "gsx_knn_exact.cuh"
 #include "gsx_masks.cuh"
+#include "gsx_radix.cuh"
 #include "gsx_sor.cuh"
 
 #include <atomic>
@@ -214,6 +215,33 @@ int gsx_sor_filter_host(const float* xyz_host, int64_t n, int32_t k, float thres
     GSX_CUDA_CHECK(cudaMemcpyAsync(mask_host, mask.p, (size_t)n, cudaMemcpyDeviceToHost, st));
     if (means_host) GSX_CUDA_CHECK(cudaMemcpyAsync(means_host, means.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     GSX_CUDA_CHECK(cudaStreamSynchronize(st));
+    return GSX_OK;
+}
+
+/* ------------------------------------------------------------------ pair sort (gpu_ops.py:227) */
+
+int64_t gsx_sort_pairs_workspace_bytes(int64_t n) {
+    if (n < 1) n = 1;
+    return (int64_t)(align_up((size_t)n * 8, 256) + align_up((size_t)n * 4, 256) + radix_ws_bytes(n) + 1024);
+}
+
+int gsx_sort_pairs(uint64_t* keys_dev, int32_t* vals_dev, int64_t n, int32_t begin_bit, int32_t end_bit, void* ws,
+                   int64_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) return GSX_OK;
+    GSX_REQUIRE(ws_bytes >= gsx_sort_pairs_workspace_bytes(n), GSX_ERR_WORKSPACE, "sort: workspace too small");
+    Carver c(ws, (size_t)ws_bytes);
+    uint64_t* k1 = c.take<uint64_t>((size_t)n);
+    int32_t* v1 = c.take<int32_t>((size_t)n);
+    char* rws = c.take<char>(radix_ws_bytes(n));
+    uint64_t* ks = nullptr;
+    int32_t* vs = nullptr;
+    int rc = radix_sort_pairs(keys_dev, k1, vals_dev, v1, n, begin_bit, end_bit, rws, radix_ws_bytes(n), &ks, &vs, st);
+    if (rc) return rc;
+    if (ks != keys_dev) {
+        GSX_CUDA_CHECK(cudaMemcpyAsync(keys_dev, ks, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+        GSX_CUDA_CHECK(cudaMemcpyAsync(vals_dev, vs, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    }
     return GSX_OK;
 }
 

@@ -16,7 +16,7 @@
 #include "gsx_knn_exact.cuh"
 #include "gsx_sor.cuh"
 
-#include <cub/device/device_radix_sort.cuh>
+#include "gsx_radix.cuh"
 #include <math.h>
 
 namespace gsx {
@@ -40,13 +40,7 @@ struct ExWs {
     bool ok;
 };
 
-static size_t ex_cub_bytes(int64_t n) {
-    size_t bytes = 0;
-    cub::DoubleBuffer<uint64_t> k(nullptr, nullptr);
-    cub::DoubleBuffer<int32_t> v(nullptr, nullptr);
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, (int)n, 0, 48, (cudaStream_t)0);
-    return bytes + 256;
-}
+static size_t ex_cub_bytes(int64_t n) { return radix_ws_bytes(n) + 256; }
 
 static ExWs ex_carve(void* ws, size_t bytes, int64_t n, size_t cub_bytes) {
     ExWs w;
@@ -324,11 +318,12 @@ int knn_exact_mean_dists(const float* xyz, int64_t n, int k, float* means, void*
     int blocks = (int)((n + 255) / 256);
     k_ex_keys<<<blocks, 256, 0, st>>>(xyz, n, mm[0], mm[1], mm[2], sc[0], sc[1], sc[2], w.keys0, w.vals0);
     GSX_KERNEL_CHECK();
-    cub::DoubleBuffer<uint64_t> kb(w.keys0, w.keys1);
-    cub::DoubleBuffer<int32_t> vb(w.vals0, w.vals1);
-    size_t tb = w.cub_bytes;
-    GSX_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(w.cub_temp, tb, kb, vb, (int)n, 0, 48, st));
-    k_ex_gather<<<blocks, 256, 0, st>>>(xyz, vb.Current(), n, w.spos, w.box[0]);
+    uint64_t* keys_sorted = nullptr;
+    int32_t* order = nullptr;
+    if ((rc = radix_sort_pairs(w.keys0, w.keys1, w.vals0, w.vals1, n, 0, 48, w.cub_temp, w.cub_bytes, &keys_sorted,
+                               &order, st)))
+        return rc;
+    k_ex_gather<<<blocks, 256, 0, st>>>(xyz, order, n, w.spos, w.box[0]);
     GSX_KERNEL_CHECK();
     for (int l = 1; l < kExLevels; ++l) {
         int64_t warps = w.cnt[l];

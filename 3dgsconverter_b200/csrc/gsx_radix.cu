@@ -1,0 +1,197 @@
+// gsx_radix.cu -- stable LSD radix sort of (uint64 key, int32 value) pairs, hand-written for sm_100a.
+//
+// Serves the hash-grid build (gpu_ops.py:227 `np.argsort(hashed)`; key = bucket hash << 18 | Morton code)
+// and the Morton ordering of the exact-KNN path.  8-bit digits; per pass:
+//   k_rs_hist    per-tile digit histogram (tile = 4096 keys, one CTA)  -> hist[digit][tile]
+//   exclusive scan of the digit-major matrix (multi-level block scan)   -> global base of (digit, tile)
+//   k_rs_scatter per-tile stable ranks: every warp owns 512 consecutive keys, ranks them 32 at a time
+//                with match.any on the digit + per-warp shared-memory counters, warps are chained by a
+//                per-digit prefix over the 8 warps, then the pairs are written to their final place.
+// Only the bits [begin_bit, end_bit) are sorted (the hash needs ceil(log2 N) bits, not 32).
+// HBM traffic per pass: 8 B (hist) + 12 B read + 12 B written per pair.
+#include "gsx_common.cuh"
+#include "gsx_radix.cuh"
+
+namespace gsx {
+
+#define GSX_FULL 0xffffffffu
+constexpr int kRsThreads = 256;
+constexpr int kRsPerThread = 16;
+constexpr int kRsTile = kRsThreads * kRsPerThread;  // 4096
+constexpr int kRsWarpKeys = 32 * kRsPerThread;      // 512 consecutive keys per warp
+constexpr int kScanBlock = 2048;                    // elements per scan CTA (256 threads x 8)
+
+// ------------------------------------------------------------------ exclusive scan (uint32, in place)
+__global__ void __launch_bounds__(256) k_scan_block(uint32_t* __restrict__ data, int64_t n,
+                                                    uint32_t* __restrict__ sums) {
+    const int64_t base = (int64_t)blockIdx.x * kScanBlock + (int64_t)threadIdx.x * 8;
+    uint32_t v[8];
+    uint32_t tsum = 0;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        v[e] = base + e < n ? data[base + e] : 0u;
+        tsum += v[e];
+    }
+    // exclusive scan of the 256 thread sums
+    uint32_t x = tsum;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(GSX_FULL, x, o);
+        if (lane >= o) x += y;
+    }
+    __shared__ uint32_t wsum[8];
+    if (lane == 31) wsum[w] = x;
+    __syncthreads();
+    uint32_t woff = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        if (i < w) woff += wsum[i];
+    uint32_t run = woff + x - tsum;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        if (base + e < n) data[base + e] = run;
+        run += v[e];
+    }
+    if (threadIdx.x == 255 && sums) sums[blockIdx.x] = run;
+}
+
+__global__ void __launch_bounds__(256) k_scan_add(uint32_t* __restrict__ data, int64_t n,
+                                                  const uint32_t* __restrict__ sums) {
+    const uint32_t add = sums[blockIdx.x];
+    const int64_t base = (int64_t)blockIdx.x * kScanBlock + (int64_t)threadIdx.x * 8;
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+        if (base + e < n) data[base + e] += add;
+}
+
+static size_t scan_ws_elems(int64_t n) {
+    size_t tot = 0;
+    while (n > kScanBlock) {
+        n = (n + kScanBlock - 1) / kScanBlock;
+        tot += (size_t)n + 64;
+    }
+    return tot + 64;
+}
+
+static int exclusive_scan_u32(uint32_t* data, int64_t n, uint32_t* ws, cudaStream_t st) {
+    int64_t blocks = (n + kScanBlock - 1) / kScanBlock;
+    if (blocks <= 1) {
+        k_scan_block<<<1, 256, 0, st>>>(data, n, nullptr);
+        GSX_KERNEL_CHECK();
+        return GSX_OK;
+    }
+    k_scan_block<<<(unsigned)blocks, 256, 0, st>>>(data, n, ws);
+    GSX_KERNEL_CHECK();
+    int rc = exclusive_scan_u32(ws, blocks, ws + blocks + 64, st);
+    if (rc) return rc;
+    k_scan_add<<<(unsigned)blocks, 256, 0, st>>>(data, n, ws);
+    GSX_KERNEL_CHECK();
+    return GSX_OK;
+}
+
+// ------------------------------------------------------------------ radix passes
+__global__ void __launch_bounds__(kRsThreads) k_rs_hist(const uint64_t* __restrict__ keys, int64_t n, int shift,
+                                                        int64_t ntiles, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[256];
+    sh[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * kRsTile;
+#pragma unroll 4
+    for (int e = 0; e < kRsPerThread; ++e) {
+        int64_t i = base + (int64_t)e * kRsThreads + threadIdx.x;
+        if (i < n) atomicAdd(&sh[(uint32_t)(keys[i] >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = sh[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kRsThreads)
+    k_rs_scatter(const uint64_t* __restrict__ keys_in, const int32_t* __restrict__ vals_in,
+                 uint64_t* __restrict__ keys_out, int32_t* __restrict__ vals_out, int64_t n, int shift,
+                 int64_t ntiles, const uint32_t* __restrict__ base_off) {
+    __shared__ uint32_t wcnt[8][256];  // per-warp digit counts, then per-warp base offsets
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int t = threadIdx.x; t < 8 * 256; t += kRsThreads) (&wcnt[0][0])[t] = 0;
+    __syncthreads();
+    const int64_t wbase = (int64_t)blockIdx.x * kRsTile + (int64_t)w * kRsWarpKeys;
+    uint64_t key[kRsPerThread];
+    uint32_t rank[kRsPerThread];  // stable rank of the key among equal digits of this warp
+    // phase A: ranks inside the warp (index order: step-major, lane-minor)
+#pragma unroll
+    for (int e = 0; e < kRsPerThread; ++e) {
+        const int64_t i = wbase + e * 32 + lane;
+        const bool act = i < n;
+        key[e] = act ? keys_in[i] : 0ull;
+        const uint32_t d = act ? ((uint32_t)(key[e] >> shift) & 255u) : (256u + lane);  // unique when inactive
+        const unsigned peers = __match_any_sync(GSX_FULL, d);
+        const uint32_t before = act ? wcnt[w][d] : 0u;
+        rank[e] = before + __popc(peers & ((1u << lane) - 1u));
+        __syncwarp();
+        if (act && (peers & ((1u << lane) - 1u)) == 0u) wcnt[w][d] = before + __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    // phase B: digit d (thread d): global base of (d, tile) + counts of the preceding warps
+    {
+        const int d = threadIdx.x;
+        uint32_t run = base_off[(size_t)d * ntiles + blockIdx.x];
+#pragma unroll
+        for (int ww = 0; ww < 8; ++ww) {
+            uint32_t c = wcnt[ww][d];
+            wcnt[ww][d] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    // phase C: write the pairs to their final position
+#pragma unroll
+    for (int e = 0; e < kRsPerThread; ++e) {
+        const int64_t i = wbase + e * 32 + lane;
+        if (i < n) {
+            const uint32_t d = (uint32_t)(key[e] >> shift) & 255u;
+            const uint32_t pos = wcnt[w][d] + rank[e];
+            keys_out[pos] = key[e];
+            vals_out[pos] = vals_in[i];
+        }
+    }
+}
+
+size_t radix_ws_bytes(int64_t n) {
+    if (n < 1) n = 1;
+    int64_t ntiles = (n + kRsTile - 1) / kRsTile;
+    size_t hist = (size_t)256 * ntiles;
+    return (hist + scan_ws_elems((int64_t)hist) + 256) * sizeof(uint32_t);
+}
+
+int radix_sort_pairs(uint64_t* keys0, uint64_t* keys1, int32_t* vals0, int32_t* vals1, int64_t n, int begin_bit,
+                     int end_bit, void* ws, size_t ws_bytes, uint64_t** keys_sorted, int32_t** vals_sorted,
+                     cudaStream_t st) {
+    GSX_REQUIRE(n >= 1 && n < 4294967296ll, GSX_ERR_ARG, "radix: n out of range");
+    GSX_REQUIRE(ws_bytes >= radix_ws_bytes(n), GSX_ERR_WORKSPACE, "radix: workspace too small");
+    GSX_REQUIRE(begin_bit >= 0 && end_bit <= 64 && begin_bit < end_bit, GSX_ERR_ARG, "radix: bad bit range");
+    const int64_t ntiles = (n + kRsTile - 1) / kRsTile;
+    uint32_t* hist = (uint32_t*)ws;
+    uint32_t* scan_ws = hist + (size_t)256 * ntiles;
+    uint64_t *kin = keys0, *kout = keys1;
+    int32_t *vin = vals0, *vout = vals1;
+    for (int shift = begin_bit; shift < end_bit; shift += 8) {
+        k_rs_hist<<<(unsigned)ntiles, kRsThreads, 0, st>>>(kin, n, shift, ntiles, hist);
+        GSX_KERNEL_CHECK();
+        int rc = exclusive_scan_u32(hist, (int64_t)256 * ntiles, scan_ws, st);
+        if (rc) return rc;
+        k_rs_scatter<<<(unsigned)ntiles, kRsThreads, 0, st>>>(kin, vin, kout, vout, n, shift, ntiles, hist);
+        GSX_KERNEL_CHECK();
+        uint64_t* tk = kin;
+        kin = kout;
+        kout = tk;
+        int32_t* tv = vin;
+        vin = vout;
+        vout = tv;
+    }
+    *keys_sorted = kin;
+    *vals_sorted = vin;
+    return GSX_OK;
+}
+
+}  // namespace gsx

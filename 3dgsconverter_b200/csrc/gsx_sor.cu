@@ -29,7 +29,10 @@
 #include "gsx_common.cuh"
 #include "gsx_sor.cuh"
 
+#include "gsx_radix.cuh"
+#ifdef GSX_USE_CUB
 #include <cub/device/device_radix_sort.cuh>
+#endif
 #include <math.h>
 
 namespace gsx {
@@ -71,12 +74,16 @@ SorWs sor_carve(void* ws, int64_t ws_bytes, int64_t n, size_t cub_bytes) {
     return w;
 }
 
-size_t sor_cub_bytes(int64_t n) {
+size_t sor_cub_bytes(int64_t n) {  // scratch of the pair sort (name kept from the CUB-based first version)
+#ifdef GSX_USE_CUB
     size_t bytes = 0;
     cub::DoubleBuffer<uint64_t> k(nullptr, nullptr);
     cub::DoubleBuffer<int32_t> v(nullptr, nullptr);
     cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, (int)n, 0, 50, (cudaStream_t)0);
     return bytes + 256;
+#else
+    return radix_ws_bytes(n) + 256;
+#endif
 }
 
 int64_t sor_workspace_bytes(int64_t n) {
@@ -245,12 +252,20 @@ int sor_build(const float* xyz, int64_t n, const float* bmin, float cell, SorWs&
     GSX_KERNEL_CHECK();
     int hash_bits = 1;
     while (((int64_t)1 << hash_bits) < n) ++hash_bits;
+#ifdef GSX_USE_CUB
     cub::DoubleBuffer<uint64_t> kb(w.keys0, w.keys1);
     cub::DoubleBuffer<int32_t> vb(w.vals0, w.vals1);
     size_t tb = w.cub_bytes;
     GSX_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(w.cub_temp, tb, kb, vb, (int)n, 0, kMortonBits + hash_bits, st));
     w.keys_sorted = kb.Current();
     w.order = vb.Current();
+#else
+    {
+        int rc = radix_sort_pairs(w.keys0, w.keys1, w.vals0, w.vals1, n, 0, kMortonBits + hash_bits, w.cub_temp,
+                                  w.cub_bytes, &w.keys_sorted, &w.order, st);
+        if (rc) return rc;
+    }
+#endif
     GSX_CUDA_CHECK(cudaMemsetAsync(w.table, 0, (size_t)n * sizeof(int2), st));
     k_sor_table<<<blocks, 256, 0, st>>>(w.keys_sorted, n, w.table);
     GSX_KERNEL_CHECK();
