@@ -6,7 +6,8 @@
 //   exclusive scan of the digit-major matrix (multi-level block scan)   -> global base of (digit, tile)
 //   k_rs_scatter per-tile stable ranks: every warp owns 512 consecutive keys, ranks them 32 at a time
 //                with match.any on the digit + per-warp shared-memory counters, warps are chained by a
-//                per-digit prefix over the 8 warps, then the pairs are written to their final place.
+//                per-digit prefix over the 8 warps; the pairs are first placed in shared memory in locally
+//                sorted order so that the final global writes are coalesced runs per digit.
 // Only the bits [begin_bit, end_bit) are sorted (the hash needs ceil(log2 N) bits, not 32).
 // HBM traffic per pass: 8 B (hist) + 12 B read + 12 B written per pair.
 #include "gsx_common.cuh"
@@ -106,23 +107,36 @@ __global__ void __launch_bounds__(kRsThreads) k_rs_hist(const uint64_t* __restri
     hist[(size_t)threadIdx.x * ntiles + blockIdx.x] = sh[threadIdx.x];
 }
 
+// dynamic shared memory of k_rs_scatter: the tile's pairs in locally sorted order + counters
+constexpr size_t kRsScatterSmem = (size_t)kRsTile * 12 + (size_t)8 * 256 * 4 + 2 * 256 * 4;
+
 __global__ void __launch_bounds__(kRsThreads)
     k_rs_scatter(const uint64_t* __restrict__ keys_in, const int32_t* __restrict__ vals_in,
                  uint64_t* __restrict__ keys_out, int32_t* __restrict__ vals_out, int64_t n, int shift,
                  int64_t ntiles, const uint32_t* __restrict__ base_off) {
-    __shared__ uint32_t wcnt[8][256];  // per-warp digit counts, then per-warp base offsets
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    uint64_t* skeys = reinterpret_cast<uint64_t*>(rs_smem);                      // [kRsTile]
+    int32_t* svals = reinterpret_cast<int32_t*>(rs_smem + (size_t)kRsTile * 8);  // [kRsTile]
+    uint32_t(*wcnt)[256] = reinterpret_cast<uint32_t(*)[256]>(rs_smem + (size_t)kRsTile * 12);  // [8][256]
+    uint32_t* dstart = reinterpret_cast<uint32_t*>(rs_smem + (size_t)kRsTile * 12 + 8 * 256 * 4);  // [256]
+    uint32_t* gbase = dstart + 256;                                                                 // [256]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int t = threadIdx.x; t < 8 * 256; t += kRsThreads) (&wcnt[0][0])[t] = 0;
     __syncthreads();
-    const int64_t wbase = (int64_t)blockIdx.x * kRsTile + (int64_t)w * kRsWarpKeys;
+    const int64_t tbase = (int64_t)blockIdx.x * kRsTile;
+    const int64_t wbase = tbase + (int64_t)w * kRsWarpKeys;
     uint64_t key[kRsPerThread];
     uint32_t rank[kRsPerThread];  // stable rank of the key among equal digits of this warp
     // phase A: ranks inside the warp (index order: step-major, lane-minor)
 #pragma unroll
     for (int e = 0; e < kRsPerThread; ++e) {
         const int64_t i = wbase + e * 32 + lane;
+        key[e] = i < n ? keys_in[i] : 0ull;
+    }
+#pragma unroll
+    for (int e = 0; e < kRsPerThread; ++e) {
+        const int64_t i = wbase + e * 32 + lane;
         const bool act = i < n;
-        key[e] = act ? keys_in[i] : 0ull;
         const uint32_t d = act ? ((uint32_t)(key[e] >> shift) & 255u) : (256u + lane);  // unique when inactive
         const unsigned peers = __match_any_sync(GSX_FULL, d);
         const uint32_t before = act ? wcnt[w][d] : 0u;
@@ -132,28 +146,58 @@ __global__ void __launch_bounds__(kRsThreads)
         __syncwarp();
     }
     __syncthreads();
-    // phase B: digit d (thread d): global base of (d, tile) + counts of the preceding warps
+    // phase B: digit d = thread d: tile count, per-warp exclusive offsets, global base
+    uint32_t dcount;
     {
         const int d = threadIdx.x;
-        uint32_t run = base_off[(size_t)d * ntiles + blockIdx.x];
+        uint32_t run = 0;
 #pragma unroll
         for (int ww = 0; ww < 8; ++ww) {
             uint32_t c = wcnt[ww][d];
             wcnt[ww][d] = run;
             run += c;
         }
+        dcount = run;
+        gbase[d] = base_off[(size_t)d * ntiles + blockIdx.x];
+    }
+    // exclusive scan of the 256 digit counts -> start of each digit in the locally sorted tile
+    {
+        uint32_t x = dcount;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(GSX_FULL, x, o);
+            if (lane >= o) x += y;
+        }
+        __shared__ uint32_t wtot[8];
+        if (lane == 31) wtot[w] = x;
+        __syncthreads();
+        uint32_t woff = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            if (i < w) woff += wtot[i];
+        dstart[threadIdx.x] = woff + x - dcount;
     }
     __syncthreads();
-    // phase C: write the pairs to their final position
+    // phase C: pairs into shared memory in locally sorted (digit-major, stable) order
 #pragma unroll
     for (int e = 0; e < kRsPerThread; ++e) {
         const int64_t i = wbase + e * 32 + lane;
         if (i < n) {
             const uint32_t d = (uint32_t)(key[e] >> shift) & 255u;
-            const uint32_t pos = wcnt[w][d] + rank[e];
-            keys_out[pos] = key[e];
-            vals_out[pos] = vals_in[i];
+            const uint32_t lp = dstart[d] + wcnt[w][d] + rank[e];
+            skeys[lp] = key[e];
+            svals[lp] = vals_in[i];
         }
+    }
+    __syncthreads();
+    // phase D: coalesced write-out: consecutive threads hold consecutive elements of a digit run
+    const int cnt = (int)(n - tbase < kRsTile ? n - tbase : kRsTile);
+    for (int j = threadIdx.x; j < cnt; j += kRsThreads) {
+        const uint64_t k = skeys[j];
+        const uint32_t d = (uint32_t)(k >> shift) & 255u;
+        const uint32_t pos = gbase[d] + ((uint32_t)j - dstart[d]);
+        keys_out[pos] = k;
+        vals_out[pos] = svals[j];
     }
 }
 
@@ -173,6 +217,7 @@ int radix_sort_pairs(uint64_t* keys0, uint64_t* keys1, int32_t* vals0, int32_t* 
     const int64_t ntiles = (n + kRsTile - 1) / kRsTile;
     uint32_t* hist = (uint32_t*)ws;
     uint32_t* scan_ws = hist + (size_t)256 * ntiles;
+    GSX_CUDA_CHECK(cudaFuncSetAttribute(k_rs_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsScatterSmem));
     uint64_t *kin = keys0, *kout = keys1;
     int32_t *vin = vals0, *vout = vals1;
     for (int shift = begin_bit; shift < end_bit; shift += 8) {
@@ -180,7 +225,7 @@ int radix_sort_pairs(uint64_t* keys0, uint64_t* keys1, int32_t* vals0, int32_t* 
         GSX_KERNEL_CHECK();
         int rc = exclusive_scan_u32(hist, (int64_t)256 * ntiles, scan_ws, st);
         if (rc) return rc;
-        k_rs_scatter<<<(unsigned)ntiles, kRsThreads, 0, st>>>(kin, vin, kout, vout, n, shift, ntiles, hist);
+        k_rs_scatter<<<(unsigned)ntiles, kRsThreads, kRsScatterSmem, st>>>(kin, vin, kout, vout, n, shift, ntiles, hist);
         GSX_KERNEL_CHECK();
         uint64_t* tk = kin;
         kin = kout;

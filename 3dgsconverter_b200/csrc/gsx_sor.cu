@@ -30,9 +30,6 @@
 #include "gsx_sor.cuh"
 
 #include "gsx_radix.cuh"
-#ifdef GSX_USE_CUB
-#include <cub/device/device_radix_sort.cuh>
-#endif
 #include <math.h>
 
 namespace gsx {
@@ -74,17 +71,7 @@ SorWs sor_carve(void* ws, int64_t ws_bytes, int64_t n, size_t cub_bytes) {
     return w;
 }
 
-size_t sor_cub_bytes(int64_t n) {  // scratch of the pair sort (name kept from the CUB-based first version)
-#ifdef GSX_USE_CUB
-    size_t bytes = 0;
-    cub::DoubleBuffer<uint64_t> k(nullptr, nullptr);
-    cub::DoubleBuffer<int32_t> v(nullptr, nullptr);
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, (int)n, 0, 50, (cudaStream_t)0);
-    return bytes + 256;
-#else
-    return radix_ws_bytes(n) + 256;
-#endif
-}
+size_t sor_cub_bytes(int64_t n) { return radix_ws_bytes(n) + 256; }  // scratch of the pair sort
 
 int64_t sor_workspace_bytes(int64_t n) {
     if (n < 1) n = 1;
@@ -161,8 +148,8 @@ __device__ __forceinline__ uint32_t spread6(uint32_t v) {  // 6 bits -> every th
 
 // gpu_ops.py:216-224: gi = floor((p - min)/cell) (float32 ops), int64 hash mod n.
 __global__ void __launch_bounds__(256) k_sor_keys(const float* __restrict__ xyz, int64_t n, float bx, float by,
-                                                  float bz, float cell, uint64_t* __restrict__ keys,
-                                                  int32_t* __restrict__ vals) {
+                                                  float bz, float cell, uint64_t M64,
+                                                  uint64_t* __restrict__ keys, int32_t* __restrict__ vals) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float fx = __fdiv_rn(__fsub_rn(xyz[3 * i], bx), cell);
@@ -170,8 +157,17 @@ __global__ void __launch_bounds__(256) k_sor_keys(const float* __restrict__ xyz,
     float fz = __fdiv_rn(__fsub_rn(xyz[3 * i + 2], bz), cell);
     float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
     int64_t gx = (int64_t)(int32_t)flx, gy = (int64_t)(int32_t)fly, gz = (int64_t)(int32_t)flz;
-    int64_t h = ((gx * 73856093LL) ^ (gy * 19349663LL) ^ (gz * 83492791LL)) % n;
-    if (h < 0) h += n;
+    int64_t hx = (gx * 73856093LL) ^ (gy * 19349663LL) ^ (gz * 83492791LL);
+    int64_t h;
+    if (hx >= 0) {  // always, since gi >= 0 for points inside the bounding box: divide by multiply-high
+        uint64_t q = __umul64hi((uint64_t)hx, M64);  // M64 = floor((2^64-1)/n): q in {true q - 2 .. true q}
+        uint64_t r = (uint64_t)hx - q * (uint64_t)n;
+        while (r >= (uint64_t)n) r -= (uint64_t)n;
+        h = (int64_t)r;
+    } else {
+        h = hx % n;
+        if (h < 0) h += n;
+    }
     // position inside the cell, 6 bits per axis (ordering only -- never affects results)
     uint32_t sx = (uint32_t)fminf(63.f, fmaxf(0.f, (fx - flx) * 64.f));
     uint32_t sy = (uint32_t)fminf(63.f, fmaxf(0.f, (fy - fly) * 64.f));
@@ -248,24 +244,16 @@ __global__ void __launch_bounds__(1024) k_sor_gather(const float* __restrict__ x
 
 int sor_build(const float* xyz, int64_t n, const float* bmin, float cell, SorWs& w, cudaStream_t st) {
     int blocks = (int)((n + 255) / 256);
-    k_sor_keys<<<blocks, 256, 0, st>>>(xyz, n, bmin[0], bmin[1], bmin[2], cell, w.keys0, w.vals0);
+    k_sor_keys<<<blocks, 256, 0, st>>>(xyz, n, bmin[0], bmin[1], bmin[2], cell, 0xFFFFFFFFFFFFFFFFull / (uint64_t)n,
+                                       w.keys0, w.vals0);
     GSX_KERNEL_CHECK();
     int hash_bits = 1;
     while (((int64_t)1 << hash_bits) < n) ++hash_bits;
-#ifdef GSX_USE_CUB
-    cub::DoubleBuffer<uint64_t> kb(w.keys0, w.keys1);
-    cub::DoubleBuffer<int32_t> vb(w.vals0, w.vals1);
-    size_t tb = w.cub_bytes;
-    GSX_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(w.cub_temp, tb, kb, vb, (int)n, 0, kMortonBits + hash_bits, st));
-    w.keys_sorted = kb.Current();
-    w.order = vb.Current();
-#else
     {
         int rc = radix_sort_pairs(w.keys0, w.keys1, w.vals0, w.vals1, n, 0, kMortonBits + hash_bits, w.cub_temp,
                                   w.cub_bytes, &w.keys_sorted, &w.order, st);
         if (rc) return rc;
     }
-#endif
     GSX_CUDA_CHECK(cudaMemsetAsync(w.table, 0, (size_t)n * sizeof(int2), st));
     k_sor_table<<<blocks, 256, 0, st>>>(w.keys_sorted, n, w.table);
     GSX_KERNEL_CHECK();
