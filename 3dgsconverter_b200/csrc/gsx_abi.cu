@@ -100,7 +100,7 @@ int64_t gsx_sor_workspace_bytes(int64_t n) { return sor_workspace_bytes(n); }
 static int carve_checked(void* ws, int64_t ws_bytes, int64_t n, SorWs& w) {
     GSX_REQUIRE(n >= 1 && n < 2147483584ll, GSX_ERR_ARG, "sor: n=%lld out of range [1, 2^31-64)", (long long)n);
     GSX_REQUIRE(ws != nullptr, GSX_ERR_WORKSPACE, "sor: null workspace");
-    w = sor_carve(ws, ws_bytes, n, sor_cub_bytes(n));
+    w = sor_carve(ws, ws_bytes, n, sor_sort_ws_bytes(n));
     GSX_REQUIRE(w.ok, GSX_ERR_WORKSPACE, "sor: workspace too small (%lld < %zu)", (long long)ws_bytes, w.total);
     return GSX_OK;
 }

@@ -34,15 +34,15 @@ struct ExWs {
     float* partial;
     float* minmax;
     unsigned int* counters;
-    char* cub_temp;
-    size_t cub_bytes;
+    char* sort_ws;
+    size_t sort_ws_bytes;
     size_t total;
     bool ok;
 };
 
-static size_t ex_cub_bytes(int64_t n) { return radix_ws_bytes(n) + 256; }
+static size_t ex_sort_ws_bytes(int64_t n) { return radix_ws_bytes(n) + 256; }
 
-static ExWs ex_carve(void* ws, size_t bytes, int64_t n, size_t cub_bytes) {
+static ExWs ex_carve(void* ws, size_t bytes, int64_t n, size_t sort_ws_bytes) {
     ExWs w;
     Carver c(ws, bytes);
     w.n = n;
@@ -60,8 +60,8 @@ static ExWs ex_carve(void* ws, size_t bytes, int64_t n, size_t cub_bytes) {
     w.partial = c.take<float>(6 * 1024);
     w.minmax = c.take<float>(8);
     w.counters = c.take<unsigned int>(64);
-    w.cub_bytes = cub_bytes;
-    w.cub_temp = c.take<char>(cub_bytes);
+    w.sort_ws_bytes = sort_ws_bytes;
+    w.sort_ws = c.take<char>(sort_ws_bytes);
     w.total = align_up(c.off, 256);
     w.ok = c.ok();
     return w;
@@ -69,7 +69,7 @@ static ExWs ex_carve(void* ws, size_t bytes, int64_t n, size_t cub_bytes) {
 
 int64_t knn_exact_workspace_bytes(int64_t n) {
     if (n < 1) n = 1;
-    ExWs w = ex_carve(nullptr, 0, n, ex_cub_bytes(n));
+    ExWs w = ex_carve(nullptr, 0, n, ex_sort_ws_bytes(n));
     return (int64_t)w.total + 1024;
 }
 
@@ -303,7 +303,7 @@ int knn_exact_mean_dists(const float* xyz, int64_t n, int k, float* means, void*
                          cudaStream_t st) {
     GSX_REQUIRE(n >= 1 && n < 2147483584ll, GSX_ERR_ARG, "knn_exact: n out of range");
     GSX_REQUIRE(k >= 1 && k <= 63, GSX_ERR_UNSUPPORTED, "knn_exact: k must be in [1,63] (got %d)", k);
-    ExWs w = ex_carve(ws, (size_t)ws_bytes, n, ex_cub_bytes(n));
+    ExWs w = ex_carve(ws, (size_t)ws_bytes, n, ex_sort_ws_bytes(n));
     GSX_REQUIRE(w.ok, GSX_ERR_WORKSPACE, "knn_exact: workspace too small");
     int rc = sor_minmax(xyz, n, w.minmax, w.partial, st);
     if (rc) return rc;
@@ -320,7 +320,7 @@ int knn_exact_mean_dists(const float* xyz, int64_t n, int k, float* means, void*
     GSX_KERNEL_CHECK();
     uint64_t* keys_sorted = nullptr;
     int32_t* order = nullptr;
-    if ((rc = radix_sort_pairs(w.keys0, w.keys1, w.vals0, w.vals1, n, 0, 48, w.cub_temp, w.cub_bytes, &keys_sorted,
+    if ((rc = radix_sort_pairs(w.keys0, w.keys1, w.vals0, w.vals1, n, 0, 48, w.sort_ws, w.sort_ws_bytes, &keys_sorted,
                                &order, st)))
         return rc;
     k_ex_gather<<<blocks, 256, 0, st>>>(xyz, order, n, w.spos, w.box[0]);

@@ -44,7 +44,7 @@ constexpr int kQueryBatch = 16;   // consecutive queries grabbed per warp
 
 // ------------------------------------------------------------------ workspace layout
 
-SorWs sor_carve(void* ws, int64_t ws_bytes, int64_t n, size_t cub_bytes) {
+SorWs sor_carve(void* ws, int64_t ws_bytes, int64_t n, size_t sort_ws_bytes) {
     SorWs w;
     Carver c(ws, (size_t)ws_bytes);
     int64_t nchunk = (n + 31) / 32, nsuper = (nchunk + 31) / 32;
@@ -62,8 +62,8 @@ SorWs sor_carve(void* ws, int64_t ws_bytes, int64_t n, size_t cub_bytes) {
     w.counters = c.take<unsigned int>(64);
     w.stats = c.take<unsigned long long>(8);
     w.meanstd = c.take<float>(8);
-    w.cub_bytes = cub_bytes;
-    w.cub_temp = c.take<char>(cub_bytes);
+    w.sort_ws_bytes = sort_ws_bytes;
+    w.sort_ws = c.take<char>(sort_ws_bytes);
     w.ms_bytes = mean_std_ws_bytes(n);
     w.ms_ws = c.take<char>(w.ms_bytes);
     w.total = align_up(c.off, 256);
@@ -71,11 +71,11 @@ SorWs sor_carve(void* ws, int64_t ws_bytes, int64_t n, size_t cub_bytes) {
     return w;
 }
 
-size_t sor_cub_bytes(int64_t n) { return radix_ws_bytes(n) + 256; }  // scratch of the pair sort
+size_t sor_sort_ws_bytes(int64_t n) { return radix_ws_bytes(n) + 256; }  // scratch of the pair sort
 
 int64_t sor_workspace_bytes(int64_t n) {
     if (n < 1) n = 1;
-    SorWs w = sor_carve(nullptr, 0, n, sor_cub_bytes(n));
+    SorWs w = sor_carve(nullptr, 0, n, sor_sort_ws_bytes(n));
     return (int64_t)w.total + 1024;
 }
 
@@ -250,8 +250,8 @@ int sor_build(const float* xyz, int64_t n, const float* bmin, float cell, SorWs&
     int hash_bits = 1;
     while (((int64_t)1 << hash_bits) < n) ++hash_bits;
     {
-        int rc = radix_sort_pairs(w.keys0, w.keys1, w.vals0, w.vals1, n, 0, kMortonBits + hash_bits, w.cub_temp,
-                                  w.cub_bytes, &w.keys_sorted, &w.order, st);
+        int rc = radix_sort_pairs(w.keys0, w.keys1, w.vals0, w.vals1, n, 0, kMortonBits + hash_bits, w.sort_ws,
+                                  w.sort_ws_bytes, &w.keys_sorted, &w.order, st);
         if (rc) return rc;
     }
     GSX_CUDA_CHECK(cudaMemsetAsync(w.table, 0, (size_t)n * sizeof(int2), st));

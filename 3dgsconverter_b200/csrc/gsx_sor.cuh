@@ -20,17 +20,17 @@ struct SorWs {
     unsigned int* counters;
     unsigned long long* stats;
     float* meanstd;
-    char* cub_temp;
-    size_t cub_bytes;
+    char* sort_ws;
+    size_t sort_ws_bytes;
     char* ms_ws;
     size_t ms_bytes;
     size_t total;
     bool ok;
 };
 
-SorWs sor_carve(void* ws, int64_t ws_bytes, int64_t n, size_t cub_bytes);
+SorWs sor_carve(void* ws, int64_t ws_bytes, int64_t n, size_t sort_ws_bytes);
 int64_t sor_workspace_bytes(int64_t n);
-size_t sor_cub_bytes(int64_t n);
+size_t sor_sort_ws_bytes(int64_t n);
 int sor_minmax(const float* xyz, int64_t n, float* minmax_dev, float* partial, cudaStream_t st);
 int sor_build(const float* xyz, int64_t n, const float* bmin, float cell, SorWs& w, cudaStream_t st);
 int sor_mean_dists(SorWs& w, int64_t q_begin, int64_t q_end, int k, int hash_mode, const float* bmin, float cell,
