@@ -5,6 +5,7 @@
 #include "../../include/gsx.h"
 
 #include "gsx_common.cuh"
+#include "gsx_compact.cuh"
 #include "gsx_density.cuh"
 #include "gsx_kmeans.cuh"
 #include "gsx_knn_exact.cuh"
@@ -296,6 +297,17 @@ double gsx_alpha_logit_threshold(double min_opacity_u8) {
     if (a < 1e-6) a = 1e-6;
     if (a > 1.0 - 1e-6) a = 1.0 - 1e-6;
     return log(a / (1.0 - a));
+}
+
+/* ------------------------------------------------------------------ compaction between filters */
+
+int64_t gsx_compact_workspace_bytes(int64_t n) { return compact_workspace_bytes(n); }
+
+int gsx_compact_points(const uint8_t* mask_dev, int64_t n, const float* xyz_dev, const float* opacity_dev,
+                       const int32_t* idx_dev, float* xyz_out_dev, float* opacity_out_dev, int32_t* idx_out_dev,
+                       int64_t* count_host, void* ws, int64_t ws_bytes, void* stream) {
+    return compact_points(mask_dev, n, xyz_dev, opacity_dev, idx_dev, xyz_out_dev, opacity_out_dev, idx_out_dev,
+                          count_host, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 /* ------------------------------------------------------------------ density */

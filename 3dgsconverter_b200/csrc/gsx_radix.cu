@@ -91,6 +91,11 @@ static int exclusive_scan_u32(uint32_t* data, int64_t n, uint32_t* ws, cudaStrea
     return GSX_OK;
 }
 
+size_t scan_workspace_bytes(int64_t n) { return scan_ws_elems(n) * sizeof(uint32_t); }
+int exclusive_scan_u32_ws(uint32_t* data, int64_t n, uint32_t* ws, cudaStream_t st) {
+    return exclusive_scan_u32(data, n, ws, st);
+}
+
 // ------------------------------------------------------------------ radix passes
 __global__ void __launch_bounds__(kRsThreads) k_rs_hist(const uint64_t* __restrict__ keys, int64_t n, int shift,
                                                         int64_t ntiles, uint32_t* __restrict__ hist) {

@@ -6,25 +6,24 @@ Public surface and behaviour follow the reference (data_processor.py:7-354): eac
 and console messages are preserved.  Host-only helpers (RGB from SH, SH capping, auto-bbox report)
 are plain NumPy and stay on the host (SURVEY §2.1 "OUT").
 
+Working set: the columns the filters read (xyz, opacity) are uploaded once and stay in HBM across the
+chain (gsx.pipeline.FilterChain); the 248-byte records are gathered on the host with the surviving row
+indices.  With ``DataProcessor.defer_compaction = True`` (what ``gsx.dropin.patch(defer=True)`` sets
+for converter.py, which ignores the filters' return values and reads ``processor.data`` once,
+converter.py:259) that host gather happens ONCE, when ``.data`` is read, and the filters return None.
+
 No CPU fallback: if the CUDA backend is unavailable the filters raise instead of silently running
 the reference's SciPy path (whose mask the reference computes and then discards -- SURVEY F5).
 """
 from __future__ import annotations
+
+import os
 
 import numpy as np
 
 from ..utils.utility_functions import debug_print, status_print
 
 _SH_C0 = 0.28209479177387814
-
-
-def _xyz(vertices) -> np.ndarray:
-    return np.column_stack((vertices["x"], vertices["y"], vertices["z"]))
-
-
-def _to_device(a: np.ndarray):
-    import torch
-    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to("cuda")
 
 
 def _require_backend():
@@ -34,64 +33,94 @@ def _require_backend():
 
 
 class DataProcessor:
+    defer_compaction = os.environ.get("GSX_DEFER_COMPACTION", "0") == "1"
+
     def __init__(self, data):
-        self.data = data
+        self._data = data
+        self._chain = None      # device-resident working set (gsx.pipeline.FilterChain)
+        self._pending = False   # host records not yet gathered with the chain's surviving indices
+
+    # ------------------------------------------------------------------ host records, lazily compacted
+    @property
+    def data(self):
+        if self._pending:
+            self._data = self._data[self._chain.indices()]
+            self._chain.rebase()
+            self._pending = False
+        return self._data
+
+    @data.setter
+    def data(self, value):
+        self._data = value
+        self._chain = None
+        self._pending = False
+
+    def _working_set(self):
+        _require_backend()
+        if self._chain is None:
+            from gsx.pipeline import FilterChain
+            v = self._data
+            xyz = np.column_stack((v["x"], v["y"], v["z"]))
+            op = v["opacity"] if "opacity" in v.dtype.names else None
+            self._chain = FilterChain(xyz, op)
+        return self._chain
+
+    def _count(self):
+        return self._chain.count if self._chain is not None else len(self._data)
+
+    def _done(self):
+        self._pending = True
+        return None if self.defer_compaction else self.data
 
     # ------------------------------------------------------------------ density (:11-117)
     def apply_density_filter(self, voxel_size=1.0, threshold_percentage=0.32, sensitivity=None,
                              keep_multicluster=False):
         debug_print("[DEBUG] Executing 'apply_density_filter' function...")
-        if not isinstance(self.data, np.ndarray):
+        if not isinstance(self._data, np.ndarray):
             raise TypeError("self.data must be a numpy structured array.")
-        _require_backend()
         from gsx import density
         if sensitivity is not None:
             voxel_size, threshold_percentage = density.slider(sensitivity)
         debug_print(f"Density Filter Params: Voxel={voxel_size:.4f}, Thresh={threshold_percentage:.4f}%, "
                     f"MultiCluster={keep_multicluster}")
-        vertices = self.data
-        if len(vertices) == 0:
+        before = self._count()
+        if before == 0:
             status_print("Warning: Density filter removed all points.")
             return self.data
-        mask, info = density.density_filter(_to_device(_xyz(vertices)), voxel_size, threshold_percentage, None,
-                                            keep_multicluster)
+        chain = self._working_set()
+        kept, info = chain.density(voxel_size, threshold_percentage, None, keep_multicluster)
         debug_print(f"[DEBUG] Found {info['voxels']} unique voxels.")
         if info["dense"] == 0 or info["clusters"] == 0:
             status_print("Warning: Density filter removed all points.")
-            self.data = self.data[:0]
-            return self.data
-        self.data = vertices[mask.cpu().numpy()]
+            return self._done()
         status_print(f"Density Filter: Kept {info['clusters']} clusters (largest: {info['max_len']} voxels).")
-        status_print(f"After density filter, retained {len(self.data)} out of {len(vertices)} vertices.")
-        return self.data
+        status_print(f"After density filter, retained {kept} out of {before} vertices.")
+        return self._done()
 
     # ------------------------------------------------------------------ SOR (:119-182)
     def remove_flyers(self, k=25, threshold_factor=10.5, chunk_size=50000, intensity=None):
         debug_print("[DEBUG] Executing 'remove_flyers' function...")
-        if not isinstance(self.data, np.ndarray):
+        if not isinstance(self._data, np.ndarray):
             raise TypeError("self.data must be a numpy structured array.")
         if intensity is not None:  # :125-134
             k = int(10 + (intensity - 1) * (40 / 9))
             threshold_factor = 20.0 - (intensity - 1) * (17.0 / 9)
         debug_print(f"SOR Filter (Remove Flyers) Params: K={k}, Sigma={threshold_factor:.2f}")
-        vertices = self.data
-        num_points = len(vertices)
-        from .gpu_ops import filter_sor_gpu
+        num_points = self._count()
         _require_backend()
         status_print("[SOR] Determining outliers on GPU (gsx / sm_100a)...")
         if num_points == 0:
             return self.data
-        gpu_mask = filter_sor_gpu(_xyz(vertices), k, threshold_factor, verbose=True)
-        if gpu_mask is None:
-            raise RuntimeError("gsx: SOR backend returned no mask")
-        self.data = vertices[gpu_mask]
-        status_print(f"After removing flyers (GPU), retained {len(self.data)} out of {num_points} vertices.")
-        return self.data
+        chain = self._working_set()
+        kept = chain.sor(int(k), float(threshold_factor), hash_mode=os.environ.get("GSX_SOR_HASH", "i32wrap"),
+                         semantics=os.environ.get("GSX_SOR_SEMANTICS", "taichi"))
+        status_print(f"After removing flyers (GPU), retained {kept} out of {num_points} vertices.")
+        return self._done()
 
     # ------------------------------------------------------------------ alpha (:184-213)
     def apply_alpha_filter(self, min_opacity_u8):
         debug_print(f"[DEBUG] Executing 'apply_alpha_filter' with min={min_opacity_u8}")
-        if "opacity" not in self.data.dtype.names:
+        if "opacity" not in self._data.dtype.names:
             status_print("Warning: No opacity channel found. Alpha filter skipped.")
             return
         limit = min_opacity_u8
@@ -100,25 +129,19 @@ class DataProcessor:
         if limit >= 255:
             self.data = self.data[:0]
             return
-        _require_backend()
-        from gsx import masks
-        original_len = len(self.data)
+        original_len = self._count()
         if original_len:
-            keep = masks.alpha_mask(_to_device(self.data["opacity"]), limit).cpu().numpy()
-            self.data = self.data[keep]
-        status_print(f"Alpha Filter (min {limit}): Retained {len(self.data)} out of {original_len} splats.")
-        return self.data
+            self._working_set().alpha(limit)
+        status_print(f"Alpha Filter (min {limit}): Retained {self._count()} out of {original_len} splats.")
+        return self._done()
 
     # ------------------------------------------------------------------ bbox (:215-231)
     def crop_by_bbox(self, min_x, min_y, min_z, max_x, max_y, max_z):
-        _require_backend()
-        from gsx import masks
-        if len(self.data):
-            keep = masks.bbox_mask(_to_device(_xyz(self.data)), min_x, min_y, min_z, max_x, max_y, max_z)
-            self.data = self.data[keep.cpu().numpy()]
-        debug_print(f"[DEBUG] Number of vertices after cropping: {len(self.data)}")
-        status_print(f"After cropping, retained {len(self.data)} vertices.")
-        return self.data
+        if self._count():
+            self._working_set().crop_by_bbox(min_x, min_y, min_z, max_x, max_y, max_z)
+        debug_print(f"[DEBUG] Number of vertices after cropping: {self._count()}")
+        status_print(f"After cropping, retained {self._count()} vertices.")
+        return self._done()
 
     # ------------------------------------------------------------------ host-only helpers (:233-354)
     @staticmethod
@@ -140,38 +163,43 @@ class DataProcessor:
 
     def add_rgb_from_sh(self):
         debug_print("[DEBUG] Executing 'add_rgb_from_sh' function...")
-        names = self.data.dtype.names
+        cur = self.data
+        names = cur.dtype.names
         if "red" in names:
             return
         if "f_dc_0" not in names and "scalar_f_dc_0" not in names:
             debug_print("[DEBUG] No SH DC components found, cannot compute RGB.")
             return
-        rgb = self._compute_rgb_from_sh(self.data)
+        rgb = self._compute_rgb_from_sh(cur)
         if rgb is None:
             return
-        out = np.empty(len(self.data), dtype=self.data.dtype.descr + [("red", "u1"), ("green", "u1"), ("blue", "u1")])
+        out = np.empty(len(cur), dtype=cur.dtype.descr + [("red", "u1"), ("green", "u1"), ("blue", "u1")])
         for nm in names:
-            out[nm] = self.data[nm]
+            out[nm] = cur[nm]
         out["red"], out["green"], out["blue"] = rgb[:, 0], rgb[:, 1], rgb[:, 2]
+        chain = self._chain            # same rows: the device working set stays valid
         self.data = out
+        self._chain = chain
 
     def cap_sh_degree(self, degree):
         """Zero the f_rest_* coefficients above `degree` (0 -> all 45, 1 -> from 9, 2 -> from 24)."""
         if degree is None or degree >= 3:
             return self.data
+        cur = self.data
         first = {0: 0, 1: 9, 2: 24}.get(degree, 45)
         for i in range(first, 45):
             nm = f"f_rest_{i}"
-            if nm in self.data.dtype.names:
-                self.data[nm] = 0.0
-        return self.data
+            if nm in cur.dtype.names:
+                cur[nm] = 0.0
+        return cur
 
     def apply_auto_bbox(self):
         """Report the tight bounding box of what is left (no change to the data)."""
-        if len(self.data) == 0:
+        cur = self.data
+        if len(cur) == 0:
             status_print("Auto-BBox: No points remaining. Bounding box is undefined.")
             return
-        lo = [np.min(self.data[a]) for a in "xyz"]
-        hi = [np.max(self.data[a]) for a in "xyz"]
+        lo = [np.min(cur[a]) for a in "xyz"]
+        hi = [np.max(cur[a]) for a in "xyz"]
         status_print(f"Auto-BBox Applied: [{lo[0]:.4f}, {lo[1]:.4f}, {lo[2]:.4f}] to "
                      f"[{hi[0]:.4f}, {hi[1]:.4f}, {hi[2]:.4f}]")

@@ -53,6 +53,8 @@ _SIGS = {
     "gsx_bbox_mask": (C.c_int, [_vp, _i64, _f32p, _vp, _vp]),
     "gsx_alpha_mask": (C.c_int, [_vp, _i64, C.c_double, _vp, _vp]),
     "gsx_alpha_logit_threshold": (C.c_double, [C.c_double]),
+    "gsx_compact_workspace_bytes": (_i64, [_i64]),
+    "gsx_compact_points": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_i64), _vp, _i64, _vp]),
     "gsx_density_workspace_bytes": (_i64, [_i64, _i64]),
     "gsx_density_voxel_count": (C.c_int, [_vp, _i64, C.c_float, _i64, _vp, _vp, _i64, C.POINTER(_i64),
                                           C.POINTER(_i64), _vp, _i64, _vp]),

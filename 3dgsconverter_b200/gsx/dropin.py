@@ -5,8 +5,8 @@
 Replaces, in the *installed* ``gsconverter.processing`` package (converter.py:10,150 and
 formats/sog.py:11 import from there):
   * ``gpu_ops.kmeans``, ``gpu_ops.filter_sor_gpu``, ``gpu_ops.HAS_TAICHI``
-  * the filter methods of ``DataProcessor`` (crop_by_bbox, apply_alpha_filter, apply_density_filter,
-    remove_flyers)
+  * the ``DataProcessor`` class (same public surface; the filters run on libgsx and keep their
+    working set in HBM; ``defer=True`` gathers the host records once, when ``.data`` is read)
 Host-only helpers and everything else of the reference stay as they are.
 """
 from __future__ import annotations
@@ -26,7 +26,7 @@ def _load_ours(modname: str, relpath: str):
     return spec, mod
 
 
-def patch(verbose: bool = False):
+def patch(verbose: bool = False, defer: bool = True):
     ref_gpu_ops = importlib.import_module("gsconverter.processing.gpu_ops")
     ref_dp = importlib.import_module("gsconverter.processing.data_processor")
     if getattr(ref_gpu_ops, "_GSX_PATCHED", False):
@@ -51,7 +51,13 @@ def patch(verbose: bool = False):
     # our data_processor does `from .gpu_ops import ...`: that now resolves to the patched reference module
     ours["data_processor"][0].loader.exec_module(ours["data_processor"][1])
     Ours = ours["data_processor"][1].DataProcessor
-    for meth in ("crop_by_bbox", "apply_alpha_filter", "apply_density_filter", "remove_flyers"):
-        setattr(ref_dp.DataProcessor, meth, getattr(Ours, meth))
+    # the whole class is replaced: the device-resident working set needs the `data` property
+    Ours.defer_compaction = bool(defer)   # converter.py ignores the filters' return values (converter.py:194-259)
+    ref_dp.DataProcessor = Ours
+    proc_pkg = importlib.import_module("gsconverter.processing")
+    proc_pkg.DataProcessor = Ours
+    conv = sys.modules.get("gsconverter.converter")
+    if conv is not None and hasattr(conv, "DataProcessor"):
+        conv.DataProcessor = Ours
     if verbose:
         print("[gsx] gsconverter.processing patched: SOR / density / bbox / alpha / K-Means run on libgsx.so")

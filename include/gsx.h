@@ -118,6 +118,15 @@ int gsx_alpha_mask(const float* opacity_dev, int64_t n, double logit_thresh, uin
  * (NumPy's SIMD log may differ by one float64 ulp; the Python plugin passes NumPy's own value). */
 double gsx_alpha_logit_threshold(double min_opacity_u8);
 
+/* ---- compaction of the filters' working set: the `vertices[mask]` steps of data_processor.py:114,149,209,
+ * 217-224 for the columns the filters read (xyz, opacity) plus the surviving ORIGINAL row indices; stable like
+ * NumPy boolean indexing.  opacity_dev/opacity_out_dev may both be NULL; idx_dev NULL = identity.
+ * *count_host = number of survivors (one 4-byte D2H sync). */
+int64_t gsx_compact_workspace_bytes(int64_t n);
+int gsx_compact_points(const uint8_t* mask_dev, int64_t n, const float* xyz_dev, const float* opacity_dev,
+                       const int32_t* idx_dev, float* xyz_out_dev, float* opacity_out_dev, int32_t* idx_out_dev,
+                       int64_t* count_host, void* ws, int64_t ws_bytes, void* stream);
+
 /* ---- density filter: data_processor.py:38-52 (voxel histogram) and :111-112 (member mask) ---- */
 int64_t gsx_density_workspace_bytes(int64_t n, int64_t cap);
 /* q = floor(xyz / f32(voxel)) -> int64 triple (data_processor.py:39); counts per voxel (:43); every voxel

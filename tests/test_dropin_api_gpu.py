@@ -93,3 +93,77 @@ def test_kmeans_plugin_semantics(cuda, gsx_lib):
     assert np.array_equal(C, small) and np.array_equal(L, np.arange(10, dtype=np.int32))
     C1, L1 = gpu_ops.kmeans(synth.attributes(50_000)["scale"].reshape(-1, 1)[:50_000], 256, max_iter=20)
     assert C1.shape == (256, 1) and L1.shape == (50_000,)
+
+
+def _oracle_chain(rec):
+    """bbox -> alpha -> density -> SOR (converter.py:194-236 order) with the oracle; returns surviving rows."""
+    import oracle
+    idx = np.arange(len(rec))
+    cur = rec
+    m = oracle.bbox_mask(cur["x"], cur["y"], cur["z"], -11, -11, -11, 11, 11, 11)
+    idx, cur = idx[m], cur[m]
+    m = oracle.alpha_mask(cur["opacity"], 5)
+    idx, cur = idx[m], cur[m]
+    m, _ = oracle.density_mask(np.column_stack((cur["x"], cur["y"], cur["z"])), sensitivity=0.5, keep_multicluster=True)
+    idx, cur = idx[m], cur[m]
+    m = oracle.sor_taichi_mask(np.column_stack((cur["x"], cur["y"], cur["z"])), 16, 2.0)
+    return idx[m]
+
+
+def test_deferred_compaction_gathers_once(cuda, gsx_lib):
+    """defer_compaction=True (what gsx.dropin.patch sets for converter.py): filters return None, the
+    248-byte records are gathered once when `.data` is read -- same rows as the eager chain."""
+    from gsconverter.processing import DataProcessor
+    rec = _records(300_000)
+    want = _oracle_chain(rec)
+    old = DataProcessor.defer_compaction
+    DataProcessor.defer_compaction = True
+    try:
+        dp = DataProcessor(rec)
+        assert dp.crop_by_bbox(-11, -11, -11, 11, 11, 11) is None
+        assert dp.apply_alpha_filter(5) is None
+        assert dp.apply_density_filter(1.0, 0.32, sensitivity=0.5, keep_multicluster=True) is None
+        assert dp._data is rec                      # nothing gathered on the host yet
+        assert dp.remove_flyers(16, 2.0) is None
+        out = dp.data
+        assert np.array_equal(out, rec[want])
+        assert dp.data is out                       # idempotent
+        dp.apply_auto_bbox()
+        dp.add_rgb_from_sh()
+        assert "red" in dp.data.dtype.names and len(dp.data) == len(want)
+        dp.remove_flyers(16, 2.0)                   # chain still valid after add_rgb (same rows)
+        assert len(dp.data) <= len(want)
+    finally:
+        DataProcessor.defer_compaction = old
+
+
+def test_filter_chain_device_indices(cuda, gsx_lib):
+    from gsx.pipeline import FilterChain
+    rec = _records(300_000)
+    want = _oracle_chain(rec)
+    ch = FilterChain(np.column_stack((rec["x"], rec["y"], rec["z"])), rec["opacity"])
+    assert np.array_equal(ch.indices(), np.arange(len(rec)))
+    ch.crop_by_bbox(-11, -11, -11, 11, 11, 11)
+    ch.alpha(5)
+    ch.density(sensitivity=0.5, keep_multicluster=True)
+    n = ch.sor(16, 2.0, hash_mode="i32wrap")
+    assert n == len(want) and np.array_equal(ch.indices(), want)
+    ch.crop_by_bbox(100, 100, 100, 101, 101, 101)          # removes everything
+    assert ch.count == 0 and len(ch.indices()) == 0
+    assert ch.sor(16, 2.0) == 0 and ch.density(sensitivity=0.5)[0] == 0
+
+
+def test_compact_points_matches_numpy(cuda, gsx_lib):
+    import torch
+    from gsx.pipeline import compact
+    rng = np.random.default_rng(4)
+    for n in (1, 31, 1024, 1025, 100_003, 3_000_000):
+        xyz = rng.standard_normal((n, 3)).astype(np.float32)
+        op = rng.standard_normal(n).astype(np.float32)
+        for p in (0.0, 0.5, 1.0):
+            mask = rng.random(n) < p
+            x, o, idx, m = compact(torch.from_numpy(mask).to(cuda), torch.from_numpy(xyz).to(cuda),
+                                   torch.from_numpy(op).to(cuda), None)
+            assert m == int(mask.sum())
+            assert np.array_equal(x.cpu().numpy(), xyz[mask]) and np.array_equal(o.cpu().numpy(), op[mask])
+            assert np.array_equal(idx.cpu().numpy(), np.flatnonzero(mask))
