@@ -300,6 +300,7 @@ def main():
         line["cpu_baseline"] = measure_cpu_baseline(xyz_np, args)
         line["other_modes"] = measure_other(xyz, ws, means, args)
         line["kmeans"] = measure_kmeans(dev)
+        line["pipeline"] = measure_pipeline(xyz_np, args)
     elif world > 1:
         line["e2e"] = measure_e2e_sharded(xyz_np, args, dev, rank, world)
     if rank == 0:
@@ -408,6 +409,41 @@ def measure_other(xyz, ws, means, args):
             ms = timed(xu, mode)
             out[f"uniform_{mode}"] = {"ms": round(ms, 3), "msplats_s": round(xu.shape[0] / ms / 1e3, 2)}
     return out
+
+
+def measure_pipeline(xyz_np, args):
+    """BASELINE configs[1] chained (converter.py:194-236 order): bbox -> alpha(5) -> density(0.5, multicluster)
+    -> SOR k=16 on the 10 M cloud through gsx.pipeline.FilterChain: pinned host xyz+opacity in, surviving row
+    indices out (the device-resident working set; host records are gathered once by the caller)."""
+    import torch
+    from gsx import synth
+    from gsx.pipeline import FilterChain
+    n = len(xyz_np)
+    op_np = synth.attributes(n, 0)["opacity"] if False else np.random.default_rng(1).normal(0, 2, n).astype(np.float32)
+    px = torch.empty((n, 3), dtype=torch.float32).pin_memory()
+    px.numpy()[:] = xyz_np
+    po = torch.empty(n, dtype=torch.float32).pin_memory()
+    po.numpy()[:] = op_np
+
+    def once():
+        ch = FilterChain(px, po)
+        c0 = ch.crop_by_bbox(-11, -11, -11, 11, 11, 11)
+        c1 = ch.alpha(5)
+        c2, _ = ch.density(sensitivity=0.5, keep_multicluster=True)
+        c3 = ch.sor(K_SOR, SIGMA, hash_mode=args.hash)
+        idx = ch.indices()
+        return (c0, c1, c2, c3, len(idx))
+    once()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        counts = once()
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / reps
+    return {"what": "bbox -> alpha(5) -> density(0.5, multicluster) -> SOR k=16, host columns in, surviving indices out",
+            "ms": round(dt * 1e3, 2), "msplats_s": round(n / dt / 1e6, 2), "survivors_per_stage": list(counts[:4]),
+            "h2d_bytes": int(n * 16), "d2h_bytes": int(counts[4] * 4)}
 
 
 def measure_kmeans(dev):
