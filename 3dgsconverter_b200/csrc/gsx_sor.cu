@@ -11,9 +11,11 @@
 //     kernel) -> {start,end} bucket table -> bounding boxes of every aligned run of 32
 //     ("chunk") and 1024 ("super") sorted points.
 //   * query kernel: one warp per query, persistent CTAs with a dynamic batch counter.
-//     Lane p<27 evaluates probe p's hash and table entry; candidates are streamed 32 at
-//     a time with one coalesced float4 load per lane; the K best d^2 live one per lane
-//     in a register (two for K>32) and are maintained with ballot + shfl.
+//     Lane p<27 evaluates probe p's hash and loads its 32-byte bucket entry {start, end, box};
+//     the probes are visited nearest box first (redux.min on the lower bound) and dropped once
+//     lb >= tau; candidates are streamed 32 at a time with one coalesced float4 load per lane;
+//     the K best d^2 live one per lane in a register (two for K>32) and are maintained with
+//     ballot + shfl insertion or a bitonic merge.
 //   * EXACT pruning: the reference's result only depends on the multiset of the K
 //     smallest distances among the probed buckets' contents (A.1 step 7).  A chunk whose
 //     box lower bound -- evaluated with the same monotone float32 op sequence as d^2 --
@@ -54,7 +56,7 @@ SorWs sor_carve(void* ws, int64_t ws_bytes, int64_t n, size_t sort_ws_bytes) {
     w.vals0 = c.take<int32_t>(n);
     w.vals1 = c.take<int32_t>(n);
     w.spos = c.take<float4>(n);
-    w.table = c.take<int2>(n);
+    w.table = c.take<float4>(2 * n);
     w.caabb = c.take<float4>(2 * nchunk);
     w.saabb = c.take<float4>(2 * nsuper);
     w.partial = c.take<float>(6 * 1024);
@@ -177,15 +179,80 @@ __global__ void __launch_bounds__(256) k_sor_keys(const float* __restrict__ xyz,
     vals[i] = (int32_t)i;
 }
 
-// gpu_ops.py:232-237: first index and size of every bucket.  table pre-zeroed: {0,0} = empty
-// (the reference's cell_start == -1 <=> cell_count == 0).
+// gpu_ops.py:232-237: first index and size of every bucket.  table pre-zeroed: start == end == 0 means
+// empty (the reference's cell_start == -1 <=> cell_count == 0).  A bucket entry is 32 bytes (one DRAM
+// sector): {start, end, lo.x, lo.y | lo.z, hi.x, hi.y, hi.z}; the box is filled by k_sor_bucket_boxes.
 __global__ void __launch_bounds__(256) k_sor_table(const uint64_t* __restrict__ keys, int64_t n,
-                                                   int2* __restrict__ table) {
+                                                   float4* __restrict__ table) {
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     uint32_t h = (uint32_t)(keys[j] >> kMortonBits);
-    if (j == 0 || (uint32_t)(keys[j - 1] >> kMortonBits) != h) table[h].x = (int)j;
-    if (j == n - 1 || (uint32_t)(keys[j + 1] >> kMortonBits) != h) table[h].y = (int)(j + 1);
+    int* e = reinterpret_cast<int*>(table + 2 * (size_t)h);
+    if (j == 0 || (uint32_t)(keys[j - 1] >> kMortonBits) != h) e[0] = (int)j;
+    if (j == n - 1 || (uint32_t)(keys[j + 1] >> kMortonBits) != h) e[1] = (int)(j + 1);
+}
+
+// Bounding box of every occupied bucket (exact over its points): lets the query kernel skip whole
+// buckets whose box is farther than the current K-th best, and visit the 27 probes nearest first.
+// Each warp scans 32 consecutive sorted positions for bucket starts and reduces each bucket it finds
+// cooperatively (stride 32 over the bucket's range).
+__global__ void __launch_bounds__(256) k_sor_bucket_boxes(const uint64_t* __restrict__ keys,
+                                                          const float4* __restrict__ spos,
+                                                          const float4* __restrict__ caabb, int64_t n,
+                                                          float4* __restrict__ table) {
+    const int lane = lane_id();
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t h = 0;
+    bool start = false;
+    if (j < n) {
+        h = (uint32_t)(keys[j] >> kMortonBits);
+        start = j == 0 || (uint32_t)(keys[j - 1] >> kMortonBits) != h;
+    }
+    unsigned m = __ballot_sync(GSX_FULL, start);
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const uint32_t hb = __shfl_sync(GSX_FULL, h, src);
+        const int64_t s = (int64_t)__shfl_sync(GSX_FULL, (int)j, src);  // n < 2^31
+        const int* e = reinterpret_cast<const int*>(table + 2 * (size_t)hb);
+        const int64_t end = e[1];
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        // chunks that lie entirely inside the bucket contribute their (already computed) box; only the
+        // ragged head and tail are reduced point by point -- keeps 10^5-point buckets cheap
+        int64_t cf = (s + 31) >> 5, cl = end >> 5;  // full chunks [cf, cl)
+        int64_t head_end = cf * 32, tail_begin = cl * 32;
+        if (cf > cl) {  // the bucket lies inside one chunk: reduce it point by point
+            head_end = end;
+            tail_begin = end;
+            cf = cl = 0;
+        }
+        for (int64_t t = s + lane; t < head_end; t += 32) {
+            float4 p = spos[t];
+            lo[0] = fminf(lo[0], p.x), lo[1] = fminf(lo[1], p.y), lo[2] = fminf(lo[2], p.z);
+            hi[0] = fmaxf(hi[0], p.x), hi[1] = fmaxf(hi[1], p.y), hi[2] = fmaxf(hi[2], p.z);
+        }
+        for (int64_t c = cf + lane; c < cl; c += 32) {
+            float4 a = caabb[2 * c], b = caabb[2 * c + 1];
+            lo[0] = fminf(lo[0], a.x), lo[1] = fminf(lo[1], a.y), lo[2] = fminf(lo[2], a.z);
+            hi[0] = fmaxf(hi[0], a.w), hi[1] = fmaxf(hi[1], b.x), hi[2] = fmaxf(hi[2], b.y);
+        }
+        for (int64_t t = tail_begin + lane; t < end; t += 32) {
+            float4 p = spos[t];
+            lo[0] = fminf(lo[0], p.x), lo[1] = fminf(lo[1], p.y), lo[2] = fminf(lo[2], p.z);
+            hi[0] = fmaxf(hi[0], p.x), hi[1] = fmaxf(hi[1], p.y), hi[2] = fmaxf(hi[2], p.z);
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[a] = fminf(lo[a], __shfl_xor_sync(GSX_FULL, lo[a], o));
+                hi[a] = fmaxf(hi[a], __shfl_xor_sync(GSX_FULL, hi[a], o));
+            }
+        if (lane == 0) {
+            float* f = reinterpret_cast<float*>(table + 2 * (size_t)hb);
+            f[2] = lo[0], f[3] = lo[1], f[4] = lo[2], f[5] = hi[0], f[6] = hi[1], f[7] = hi[2];
+        }
+    }
 }
 
 // gpu_ops.py:228: sorted_pos = pos[sort_order], as float4 with w = original index; plus the boxes.
@@ -254,10 +321,12 @@ int sor_build(const float* xyz, int64_t n, const float* bmin, float cell, SorWs&
                                   w.sort_ws_bytes, &w.keys_sorted, &w.order, st);
         if (rc) return rc;
     }
-    GSX_CUDA_CHECK(cudaMemsetAsync(w.table, 0, (size_t)n * sizeof(int2), st));
+    GSX_CUDA_CHECK(cudaMemsetAsync(w.table, 0, (size_t)n * 2 * sizeof(float4), st));
     k_sor_table<<<blocks, 256, 0, st>>>(w.keys_sorted, n, w.table);
     GSX_KERNEL_CHECK();
     k_sor_gather<<<(int)((n + 1023) / 1024), 1024, 0, st>>>(xyz, w.order, n, w.spos, w.caabb, w.saabb);
+    GSX_KERNEL_CHECK();
+    k_sor_bucket_boxes<<<blocks, 256, 0, st>>>(w.keys_sorted, w.spos, w.caabb, n, w.table);
     GSX_KERNEL_CHECK();
     return GSX_OK;
 }
@@ -383,7 +452,7 @@ __device__ __forceinline__ void scan32(const float4* __restrict__ spos, int64_t 
 #endif
 template <int NREG, bool STATS>
 __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
-    k_sor_knn(const float4* __restrict__ spos, const int2* __restrict__ table, const float4* __restrict__ caabb,
+    k_sor_knn(const float4* __restrict__ spos, const float4* __restrict__ table, const float4* __restrict__ caabb,
               const float4* __restrict__ saabb, float* __restrict__ final_means, unsigned int* __restrict__ work,
               int64_t q_begin, int64_t q_end, int K, int hash_mode, float bx, float by, float bz, float cell,
               uint32_t n, uint64_t M, unsigned long long* __restrict__ stats) {
@@ -402,8 +471,8 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
         // the 27 probes of a query depend only on its cell: consecutive hash-sorted queries mostly share
         // it, so the hashes and table entries are recomputed only when the cell changes
         int cgx = 0x7fffffff, cgy = 0, cgz = 0;
-        int ps = 0, pc = 0;
-        unsigned live = 0;  // probes with a non-empty bucket
+        int ps = 0, pc = 0;                                  // lane p: bucket range of probe p
+        float blx = 0.f, bly = 0.f, blz = 0.f, bhx = 0.f, bhy = 0.f, bhz = 0.f;  // and its bounding box
 #pragma unroll 1
         for (int64_t i = qb; i < qe; ++i) {
             const float4 q = __ldg(spos + i);
@@ -419,11 +488,11 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
                 ps = 0, pc = 0;
                 if (lane < 27) {
                     uint32_t h = probe_hash(gx + pdx, gy + pdy, gz + pdz, n, M, hash_mode);
-                    int2 t = __ldg(table + h);
-                    ps = t.x;
-                    pc = t.y - t.x;
+                    const float4 t0 = __ldg(table + 2 * (size_t)h), t1 = __ldg(table + 2 * (size_t)h + 1);
+                    ps = __float_as_int(t0.x);
+                    pc = __float_as_int(t0.y) - ps;
+                    blx = t0.z, bly = t0.w, blz = t1.x, bhx = t1.y, bhy = t1.z, bhz = t1.w;
                 }
-                live = __ballot_sync(GSX_FULL, pc > 0);
             }
             if (STATS) {
                 int tot = pc;
@@ -435,12 +504,22 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
             TopK<NREG> tk;
             tk.init(K);
 
+            // lower bound of d^2 to the bucket's box (same monotone op sequence as d^2 itself, see box_lb):
+            // probes are visited nearest box first and dropped as soon as lb >= tau.  The query's own bucket
+            // has lb == 0 and therefore comes first whenever the centre probe reaches it.
+            unsigned pkey = 0xffffffffu;
+            if (pc > 0) {
+                float dx = fmaxf(fmaxf(__fsub_rn(blx, q.x), __fsub_rn(q.x, bhx)), 0.f);
+                float dy = fmaxf(fmaxf(__fsub_rn(bly, q.y), __fsub_rn(q.y, bhy)), 0.f);
+                float dz = fmaxf(fmaxf(__fsub_rn(blz, q.z), __fsub_rn(q.z, bhz)), 0.f);
+                pkey = __float_as_uint(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+            }
+
             // seed from the chunk that holds the query itself when its own bucket is big: gives a
             // tight tau before the box walk.  Only legal if the centre probe really reaches the
             // query's bucket range (with the wrapped hash it may not).
             int skip_chunk = -1;
-            unsigned todo = live;
-            if (todo & (1u << 13)) {
+            {
                 int s13 = __shfl_sync(GSX_FULL, ps, 13), c13 = __shfl_sync(GSX_FULL, pc, 13);
                 if (c13 > kSmallBucket && i >= s13 && i < (int64_t)s13 + c13) {
                     skip_chunk = (int)(i >> 5);
@@ -451,10 +530,11 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
             }
 
 #pragma unroll 1
-            while (todo) {
-                // centre bucket first (closest candidates -> tight tau early), then ascending probe index
-                const int p = (todo & (1u << 13)) ? 13 : __ffs(todo) - 1;
-                todo &= ~(1u << p);
+            for (;;) {
+                const unsigned mp = __reduce_min_sync(GSX_FULL, pkey);
+                if (mp == 0xffffffffu || !(__uint_as_float(mp) < tk.tau)) break;
+                const int p = __ffs(__ballot_sync(GSX_FULL, pkey == mp)) - 1;
+                if (lane == p) pkey = 0xffffffffu;
                 const int s = __shfl_sync(GSX_FULL, ps, p), c = __shfl_sync(GSX_FULL, pc, p);
                 const int64_t e = (int64_t)s + c;
                 if (c <= kSmallBucket) {

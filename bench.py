@@ -243,12 +243,13 @@ def main():
     kept = int(mask.sum().item())
 
     # ---- roofline of the dominant kernel (k_sor_knn): gather-model algorithmic bytes of OUR algorithm
-    # B = queries*(16 own float4 + 27*8 table probes + 4 result) + 16*candidates scanned + 32*boxes tested,
+    # B = queries*(16 own float4 + 27*32 bucket entries {start,end,box} + 4 result) + 16*candidates scanned
+    #     + 32*chunk/super boxes tested,
     # counted exactly by the instrumented build of the same kernel.
     grid = sor.build_grid(xyz if world == 1 else gd._all_gather_rows(xyz)[0], ws)
     qr = gd.query_range(n_total, rank, world)
     _, st = sor.mean_dists(grid, K_SOR, args.hash, out=means, want_stats=True, q_range=qr)
-    alg_bytes = st["queries"] * (16 + 27 * 8 + 4) + 16 * st["scanned"] + 32 * st["box_tests"]
+    alg_bytes = st["queries"] * (16 + 27 * 32 + 4) + 16 * st["scanned"] + 32 * st["box_tests"]
     ref_model_bytes = st["queries"] * (16 + 27 * 8 + 4) + 16 * st["visits"]
     knn_avg_ms = float(np.mean(knn_ms))
     peaks = {}
