@@ -150,6 +150,37 @@ int gsx_sor_build(const float* xyz_dev, int64_t n, const float* bmin_host, float
     return sor_build(xyz_dev, n, bmin_host, cell, w, (cudaStream_t)stream);
 }
 
+int gsx_sor_dist_local_run(const float* xyz_local_dev, int64_t n_local, int64_t idx_base, int64_t n_global,
+                           const float* bmin_host, float cell, uint64_t* keys_out_dev, float* pos4_out_dev, void* ws,
+                           int64_t ws_bytes, void* stream) {
+    if (n_local == 0) return GSX_OK;
+    SorWs w;
+    int rc = carve_checked(ws, ws_bytes, n_local, w);
+    if (rc) return rc;
+    GSX_REQUIRE(n_global >= n_local && n_global < 2147483584ll, GSX_ERR_ARG, "sor: bad n_global");
+    return sor_dist_local_run(xyz_local_dev, n_local, idx_base, n_global, bmin_host, cell, keys_out_dev,
+                              (float4*)pos4_out_dev, w, (cudaStream_t)stream);
+}
+
+int gsx_sor_dist_merge(const uint64_t* keys_dev, const float* pos4_dev, int64_t m, int64_t n_global,
+                       float* pos4_sorted_dev, void* ws, int64_t ws_bytes, void* stream) {
+    if (m == 0) return GSX_OK;
+    SorWs w;
+    int rc = carve_checked(ws, ws_bytes, m, w);
+    if (rc) return rc;
+    return sor_dist_merge(keys_dev, (const float4*)pos4_dev, m, n_global, (float4*)pos4_sorted_dev, w,
+                          (cudaStream_t)stream);
+}
+
+int gsx_sor_build_from_sorted(const float* spos4_dev, int64_t n, const float* bmin_host, float cell, void* ws,
+                              int64_t ws_bytes, void* stream) {
+    SorWs w;
+    int rc = carve_checked(ws, ws_bytes, n, w);
+    if (rc) return rc;
+    GSX_REQUIRE(cell > 0.f, GSX_ERR_ARG, "sor: cell size must be > 0");
+    return sor_build_from_sorted((const float4*)spos4_dev, n, bmin_host, cell, w, (cudaStream_t)stream);
+}
+
 int gsx_sor_mean_dists_range(int64_t n, int64_t q_begin, int64_t q_end, int32_t k, int32_t hash_mode,
                              const float* bmin_host, float cell, void* ws, int64_t ws_bytes, float* final_means_dev,
                              unsigned long long* stats_dev, void* stream) {

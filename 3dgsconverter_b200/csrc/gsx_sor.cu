@@ -331,6 +331,198 @@ int sor_build(const float* xyz, int64_t n, const float* bmin, float cell, SorWs&
     return GSX_OK;
 }
 
+// ------------------------------------------------------------------ distributed build (one process per GPU)
+// Bucket-range ownership: rank o owns the buckets [ceil(o*N/G), ceil((o+1)*N/G)).  Every rank sorts its own
+// slab by the GLOBAL bucket key, the runs are exchanged by owner (all-to-all, host side: gsx/dist.py), each
+// owner sorts what it received, the sorted float4 segments are all-gathered, and every rank fills its table,
+// boxes and bucket boxes from the (now identical) sorted array.  The sort work per rank drops from N to 2N/G.
+
+// stage A: keys of a local slab with hash mod n_global; payload = local index
+__global__ void __launch_bounds__(256) k_sor_keys_slab(const float* __restrict__ xyz, int64_t n, int64_t n_global,
+                                                       float bx, float by, float bz, float cell, uint64_t M64,
+                                                       uint64_t* __restrict__ keys, int32_t* __restrict__ vals) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float fx = __fdiv_rn(__fsub_rn(xyz[3 * i], bx), cell);
+    float fy = __fdiv_rn(__fsub_rn(xyz[3 * i + 1], by), cell);
+    float fz = __fdiv_rn(__fsub_rn(xyz[3 * i + 2], bz), cell);
+    float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+    int64_t gx = (int64_t)(int32_t)flx, gy = (int64_t)(int32_t)fly, gz = (int64_t)(int32_t)flz;
+    int64_t hx = (gx * 73856093LL) ^ (gy * 19349663LL) ^ (gz * 83492791LL);
+    int64_t h;
+    if (hx >= 0) {
+        uint64_t q = __umul64hi((uint64_t)hx, M64);
+        uint64_t r = (uint64_t)hx - q * (uint64_t)n_global;
+        while (r >= (uint64_t)n_global) r -= (uint64_t)n_global;
+        h = (int64_t)r;
+    } else {
+        h = hx % n_global;
+        if (h < 0) h += n_global;
+    }
+    uint32_t sx = (uint32_t)fminf(63.f, fmaxf(0.f, (fx - flx) * 64.f));
+    uint32_t sy = (uint32_t)fminf(63.f, fmaxf(0.f, (fy - fly) * 64.f));
+    uint32_t sz = (uint32_t)fminf(63.f, fmaxf(0.f, (fz - flz) * 64.f));
+    uint32_t mort = (spread6(sx) << 2) | (spread6(sy) << 1) | spread6(sz);
+    keys[i] = ((uint64_t)h << kMortonBits) | (uint64_t)mort;
+    vals[i] = (int32_t)i;
+}
+
+__global__ void __launch_bounds__(256) k_sor_gather_slab(const float* __restrict__ xyz,
+                                                         const int32_t* __restrict__ order,
+                                                         const uint64_t* __restrict__ keys_sorted, int64_t n,
+                                                         int64_t idx_base, float4* __restrict__ pos4,
+                                                         uint64_t* __restrict__ keys_out) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    int32_t idx = order[j];
+    pos4[j] = make_float4(xyz[3 * (int64_t)idx], xyz[3 * (int64_t)idx + 1], xyz[3 * (int64_t)idx + 2],
+                          __int_as_float((int)(idx_base + idx)));
+    keys_out[j] = keys_sorted[j];
+}
+
+static int hash_bits_of(int64_t n) {
+    int b = 1;
+    while (((int64_t)1 << b) < n) ++b;
+    return b;
+}
+
+int sor_dist_local_run(const float* xyz, int64_t n_local, int64_t idx_base, int64_t n_global, const float* bmin,
+                       float cell, uint64_t* keys_out, float4* pos4_out, SorWs& w, cudaStream_t st) {
+    if (n_local == 0) return GSX_OK;
+    int blocks = (int)((n_local + 255) / 256);
+    k_sor_keys_slab<<<blocks, 256, 0, st>>>(xyz, n_local, n_global, bmin[0], bmin[1], bmin[2], cell,
+                                            0xFFFFFFFFFFFFFFFFull / (uint64_t)n_global, w.keys0, w.vals0);
+    GSX_KERNEL_CHECK();
+    uint64_t* ks = nullptr;
+    int32_t* order = nullptr;
+    int rc = radix_sort_pairs(w.keys0, w.keys1, w.vals0, w.vals1, n_local, 0, kMortonBits + hash_bits_of(n_global),
+                              w.sort_ws, w.sort_ws_bytes, &ks, &order, st);
+    if (rc) return rc;
+    k_sor_gather_slab<<<blocks, 256, 0, st>>>(xyz, order, ks, n_local, idx_base, pos4_out, keys_out);
+    GSX_KERNEL_CHECK();
+    return GSX_OK;
+}
+
+// stage B: order the received runs of this rank's bucket range
+__global__ void __launch_bounds__(256) k_iota(int32_t* __restrict__ v, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = (int32_t)i;
+}
+__global__ void __launch_bounds__(256) k_gather4(const float4* __restrict__ in, const int32_t* __restrict__ order,
+                                                 int64_t n, float4* __restrict__ out) {
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) out[j] = in[order[j]];
+}
+
+int sor_dist_merge(const uint64_t* keys_in, const float4* pos4_in, int64_t m, int64_t n_global, float4* pos4_out,
+                   SorWs& w, cudaStream_t st) {
+    if (m == 0) return GSX_OK;
+    int blocks = (int)((m + 255) / 256);
+    GSX_CUDA_CHECK(cudaMemcpyAsync(w.keys0, keys_in, (size_t)m * 8, cudaMemcpyDeviceToDevice, st));
+    k_iota<<<blocks, 256, 0, st>>>(w.vals0, m);
+    GSX_KERNEL_CHECK();
+    uint64_t* ks = nullptr;
+    int32_t* order = nullptr;
+    int rc = radix_sort_pairs(w.keys0, w.keys1, w.vals0, w.vals1, m, 0, kMortonBits + hash_bits_of(n_global), w.sort_ws,
+                              w.sort_ws_bytes, &ks, &order, st);
+    if (rc) return rc;
+    k_gather4<<<blocks, 256, 0, st>>>(pos4_in, order, m, pos4_out);
+    GSX_KERNEL_CHECK();
+    return GSX_OK;
+}
+
+// stage C: everything gsx_sor_build produces, from an already hash-sorted float4 array
+__global__ void __launch_bounds__(256) k_sor_keys_sorted(const float4* __restrict__ spos, int64_t n, float bx, float by,
+                                                         float bz, float cell, uint64_t M64,
+                                                         uint64_t* __restrict__ keys) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = spos[i];
+    int64_t gx = (int64_t)(int32_t)floorf(__fdiv_rn(__fsub_rn(p.x, bx), cell));
+    int64_t gy = (int64_t)(int32_t)floorf(__fdiv_rn(__fsub_rn(p.y, by), cell));
+    int64_t gz = (int64_t)(int32_t)floorf(__fdiv_rn(__fsub_rn(p.z, bz), cell));
+    int64_t hx = (gx * 73856093LL) ^ (gy * 19349663LL) ^ (gz * 83492791LL);
+    int64_t h;
+    if (hx >= 0) {
+        uint64_t q = __umul64hi((uint64_t)hx, M64);
+        uint64_t r = (uint64_t)hx - q * (uint64_t)n;
+        while (r >= (uint64_t)n) r -= (uint64_t)n;
+        h = (int64_t)r;
+    } else {
+        h = hx % n;
+        if (h < 0) h += n;
+    }
+    keys[i] = (uint64_t)h << kMortonBits;
+}
+
+// chunk / super boxes of an already sorted array (the box part of k_sor_gather)
+__global__ void __launch_bounds__(1024) k_sor_boxes_sorted(const float4* __restrict__ spos, int64_t n,
+                                                           float4* __restrict__ caabb, float4* __restrict__ saabb) {
+    int64_t j = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    if (j < n) {
+        float4 p = spos[j];
+        lo[0] = hi[0] = p.x;
+        lo[1] = hi[1] = p.y;
+        lo[2] = hi[2] = p.z;
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(GSX_FULL, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(GSX_FULL, hi[a], o));
+        }
+    __shared__ float sm[6][32];
+    int w = threadIdx.x >> 5;
+    int64_t chunk = (int64_t)blockIdx.x * 32 + w;
+    if (lane_id() == 0) {
+        if (chunk * 32 < n) {
+            caabb[2 * chunk] = make_float4(lo[0], lo[1], lo[2], hi[0]);
+            caabb[2 * chunk + 1] = make_float4(hi[1], hi[2], 0.f, 0.f);
+        }
+        for (int a = 0; a < 3; ++a) {
+            sm[a][w] = lo[a];
+            sm[3 + a][w] = hi[a];
+        }
+    }
+    __syncthreads();
+    if (w == 0) {
+        float v[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            v[a] = sm[a][lane_id()];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                float t = __shfl_xor_sync(GSX_FULL, v[a], o);
+                v[a] = a < 3 ? fminf(v[a], t) : fmaxf(v[a], t);
+            }
+        }
+        if (lane_id() == 0) {
+            saabb[2 * (int64_t)blockIdx.x] = make_float4(v[0], v[1], v[2], v[3]);
+            saabb[2 * (int64_t)blockIdx.x + 1] = make_float4(v[4], v[5], 0.f, 0.f);
+        }
+    }
+}
+
+int sor_build_from_sorted(const float4* spos_in, int64_t n, const float* bmin, float cell, SorWs& w, cudaStream_t st) {
+    int blocks = (int)((n + 255) / 256);
+    if (spos_in != w.spos)
+        GSX_CUDA_CHECK(cudaMemcpyAsync(w.spos, spos_in, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+    k_sor_keys_sorted<<<blocks, 256, 0, st>>>(w.spos, n, bmin[0], bmin[1], bmin[2], cell,
+                                              0xFFFFFFFFFFFFFFFFull / (uint64_t)n, w.keys0);
+    GSX_KERNEL_CHECK();
+    w.keys_sorted = w.keys0;
+    GSX_CUDA_CHECK(cudaMemsetAsync(w.table, 0, (size_t)n * 2 * sizeof(float4), st));
+    k_sor_table<<<blocks, 256, 0, st>>>(w.keys_sorted, n, w.table);
+    GSX_KERNEL_CHECK();
+    k_sor_boxes_sorted<<<(int)((n + 1023) / 1024), 1024, 0, st>>>(w.spos, n, w.caabb, w.saabb);
+    GSX_KERNEL_CHECK();
+    k_sor_bucket_boxes<<<blocks, 256, 0, st>>>(w.keys_sorted, w.spos, w.caabb, n, w.table);
+    GSX_KERNEL_CHECK();
+    return GSX_OK;
+}
+
 // ------------------------------------------------------------------ query kernel
 
 // gpu_ops.py:130-132 probe hash.  mode 0: int32 wrapping products (Taichi default_ip), Python-style

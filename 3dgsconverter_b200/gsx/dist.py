@@ -152,3 +152,87 @@ def density_filter_sharded(xyz_local: torch.Tensor, voxel_size=1.0, threshold_pe
     keep, n_kept, max_len = density.select_clusters(vox, keep_multicluster)
     mask = ops.member_mask(xyz_local, voxel_size, keep)
     return mask, dict(clusters=n_kept, max_len=max_len, dense=len(vox), voxels=n_unique)
+
+
+# ------------------------------------------------------------------ distributed grid build (bucket-range ownership)
+def _owner_bounds(n_global: int, world: int):
+    """First bucket of every owner: rank o owns the buckets [ceil(o*N/G), ceil((o+1)*N/G))."""
+    return [(o * n_global + world - 1) // world for o in range(world + 1)]
+
+
+def build_grid_distributed(xyz_local: torch.Tensor, group=None):
+    """Hash grid of the UNION cloud without replicating the sort: local sort of the slab by global bucket key
+    -> all-to-all by bucket owner -> owner-local sort -> all-gather of the sorted float4 segments ->
+    table / boxes filled locally.  Returns (SorGrid over n_global points, sizes of the slabs)."""
+    import ctypes as C
+    from . import sor
+    from ._abi import lib, check
+    from .sor import _ptr, _stream
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = xyz_local.device
+    n_local = xyz_local.shape[0]
+    sizes_t = torch.zeros(world, dtype=torch.int64, device=dev)
+    sizes_t[rank] = n_local
+    dist.all_reduce(sizes_t, group=group)
+    sizes = [int(v) for v in sizes_t.tolist()]
+    n_global = sum(sizes)
+    idx_base = sum(sizes[:rank])
+    # global bounding box -> cell size (gpu_ops.py:203-213 on the union cloud)
+    lo = xyz_local.min(dim=0).values if n_local else torch.full((3,), float("inf"), device=dev)
+    hi = xyz_local.max(dim=0).values if n_local else torch.full((3,), float("-inf"), device=dev)
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
+    mm = torch.cat([lo, hi]).cpu().numpy().astype(np.float32)
+    cell = float(lib.gsx_sor_cell_size(mm.ctypes.data_as(C.POINTER(C.c_float)), n_global))
+    bmin = mm[:3].copy()
+    bminp = bmin.ctypes.data_as(C.POINTER(C.c_float))
+    # A. local sorted run
+    ws_l = sor.workspace(max(n_local, 1), dev)
+    keys = torch.empty(n_local, dtype=torch.int64, device=dev)
+    pos4 = torch.empty((n_local, 4), dtype=torch.float32, device=dev)
+    check(lib.gsx_sor_dist_local_run(_ptr(xyz_local), n_local, idx_base, n_global, bminp, cell, _ptr(keys), _ptr(pos4),
+                                     _ptr(ws_l), ws_l.numel(), _stream()), "gsx_sor_dist_local_run")
+    # split by owner (keys are sorted; owner boundaries are monotone in the key)
+    bounds = torch.tensor([b << 18 for b in _owner_bounds(n_global, world)], dtype=torch.int64, device=dev)
+    cut = torch.searchsorted(keys, bounds)          # [world+1] positions
+    send = (cut[1:] - cut[:-1]).to(torch.int64)
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)
+    send_l, recv_l = [int(v) for v in send.tolist()], [int(v) for v in recv.tolist()]
+    m = sum(recv_l)
+    keys_r = torch.empty(m, dtype=torch.int64, device=dev)
+    pos4_r = torch.empty((m, 4), dtype=torch.float32, device=dev)
+    dist.all_to_all_single(keys_r, keys, recv_l, send_l, group=group)
+    dist.all_to_all_single(pos4_r, pos4, recv_l, send_l, group=group)
+    # B. owner-local ordering of the received runs
+    seg = torch.empty((m, 4), dtype=torch.float32, device=dev)
+    ws_m = ws_l if m <= n_local else sor.workspace(max(m, 1), dev)
+    check(lib.gsx_sor_dist_merge(_ptr(keys_r), _ptr(pos4_r), m, n_global, _ptr(seg), _ptr(ws_m), ws_m.numel(),
+                                 _stream()), "gsx_sor_dist_merge")
+    # all-gather of the sorted segments in owner order = the globally sorted array
+    spos_full, seg_sizes = _all_gather_rows(seg, group)
+    assert spos_full.shape[0] == n_global
+    # C. table, boxes, bucket boxes -- replicated, linear in n_global
+    ws = sor.workspace(n_global, dev)
+    check(lib.gsx_sor_build_from_sorted(_ptr(spos_full), n_global, bminp, cell, _ptr(ws), ws.numel(), _stream()),
+          "gsx_sor_build_from_sorted")
+    return sor.SorGrid(n_global, ws, bmin, cell), sizes
+
+
+def sor_filter_sharded_v2(xyz_local: torch.Tensor, k: int = 25, threshold_factor: float = 1.0,
+                          hash_mode: str | None = None, group=None, return_means: bool = False):
+    """Like sor_filter_sharded, with the distributed grid build (no replicated sort, no all-gather of raw xyz)."""
+    from . import sor
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    grid, sizes = build_grid_distributed(xyz_local, group)
+    n = grid.n
+    qb, qe = query_range(n, rank, world)
+    means = torch.zeros(n, dtype=torch.float32, device=xyz_local.device)
+    sor.mean_dists(grid, k, hash_mode, out=means, q_range=(qb, qe))
+    dist.all_reduce(means, op=dist.ReduceOp.SUM, group=group)
+    mask_all = sor.threshold_mask(means, sor.mean_std(means), threshold_factor)
+    off = sum(sizes[:rank])
+    sl = slice(off, off + sizes[rank])
+    return (mask_all[sl], means[sl]) if return_means else mask_all[sl]

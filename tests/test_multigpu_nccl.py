@@ -26,6 +26,8 @@ def _worker(rank, world, port, n_per, q):
     for mode in ("i32wrap", "i64"):
         mask, means = gd.sor_filter_sharded(local, 16, 2.0, mode, return_means=True)
         res[f"sor_{mode}"] = (mask.cpu().numpy(), means.cpu().numpy())
+        mask2, means2 = gd.sor_filter_sharded_v2(local, 16, 2.0, mode, return_means=True)
+        res[f"sor2_{mode}"] = (mask2.cpu().numpy(), means2.cpu().numpy())
     dm, info = gd.density_filter_sharded(local, sensitivity=0.5, keep_multicluster=True)
     res["density"] = (dm.cpu().numpy(), info["clusters"])
     if rank == 0:  # single-GPU truth on the union cloud
@@ -66,6 +68,10 @@ def test_sharded_equals_single_gpu(gsx_lib):
         gmd = np.concatenate([res[r][f"sor_{mode}"][1] for r in range(world)])
         assert np.array_equal(gmd.view(np.uint32), tmd.view(np.uint32)), mode
         assert np.array_equal(gm, tm), mode
+        gm2 = np.concatenate([res[r][f"sor2_{mode}"][0] for r in range(world)])
+        gmd2 = np.concatenate([res[r][f"sor2_{mode}"][1] for r in range(world)])
+        assert np.array_equal(gmd2.view(np.uint32), tmd.view(np.uint32)), ("distributed build", mode)
+        assert np.array_equal(gm2, tm), ("distributed build", mode)
     td, tc = res[0]["truth_density"]
     gd_ = np.concatenate([res[r]["density"][0] for r in range(world)])
     assert np.array_equal(gd_, td) and all(res[r]["density"][1] == tc for r in range(world))

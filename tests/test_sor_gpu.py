@@ -91,3 +91,39 @@ def test_mean_std_matches_numpy(cuda, gsx_lib):
         got = sor.mean_std(torch.from_numpy(a).to(cuda)).cpu().numpy()
         want = np.array([np.mean(a), np.std(a)], dtype=np.float32)
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), n
+
+
+def test_build_from_sorted_equals_build(cuda, gsx_lib):
+    """Stage C of the distributed build on one GPU: local run -> merge -> build_from_sorted must give the
+    same mean distances as the one-shot build (world size 1 degenerates to exactly this)."""
+    import ctypes as C
+    import torch
+    import oracle
+    from gsx import sor, synth
+    from gsx._abi import lib, check
+    from gsx.sor import _ptr, _stream
+    xyz_np = synth.xyz(200_000, "mixed")
+    xyz = torch.from_numpy(xyz_np).to(cuda)
+    n = xyz.shape[0]
+    ref = sor.build_grid(xyz)
+    bminp = ref.bmin.ctypes.data_as(C.POINTER(C.c_float))
+    ws = sor.workspace(n, cuda)
+    keys = torch.empty(n, dtype=torch.int64, device=cuda)
+    pos4 = torch.empty((n, 4), dtype=torch.float32, device=cuda)
+    check(lib.gsx_sor_dist_local_run(_ptr(xyz), n, 0, n, bminp, ref.cell, _ptr(keys), _ptr(pos4), _ptr(ws), ws.numel(),
+                                     _stream()))
+    assert bool((keys[1:] >= keys[:-1]).all())
+    # split in two "source ranks" and merge them back (exercises stage B)
+    half = n // 2
+    perm_keys = torch.cat([keys[half:], keys[:half]])
+    perm_pos = torch.cat([pos4[half:], pos4[:half]])
+    seg = torch.empty_like(pos4)
+    check(lib.gsx_sor_dist_merge(_ptr(perm_keys), _ptr(perm_pos), n, n, _ptr(seg), _ptr(ws), ws.numel(), _stream()))
+    ws2 = sor.workspace(n, cuda)
+    check(lib.gsx_sor_build_from_sorted(_ptr(seg), n, bminp, ref.cell, _ptr(ws2), ws2.numel(), _stream()))
+    grid2 = sor.SorGrid(n, ws2, ref.bmin, ref.cell)
+    for mode in ("i32wrap", "i64"):
+        a = sor.mean_dists(ref, 16, mode).cpu().numpy()
+        b = sor.mean_dists(grid2, 16, mode).cpu().numpy()
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+        assert np.array_equal(a.view(np.uint32), oracle.sor_taichi_mean_dists(xyz_np, 16, mode).view(np.uint32))
