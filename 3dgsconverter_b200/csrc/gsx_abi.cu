@@ -151,25 +151,30 @@ int gsx_sor_build(const float* xyz_dev, int64_t n, const float* bmin_host, float
 }
 
 int gsx_sor_dist_local_run(const float* xyz_local_dev, int64_t n_local, int64_t idx_base, int64_t n_global,
-                           const float* bmin_host, float cell, uint64_t* keys_out_dev, float* pos4_out_dev, void* ws,
-                           int64_t ws_bytes, void* stream) {
-    if (n_local == 0) return GSX_OK;
+                           int32_t world, const float* bmin_host, float cell, float* pos4_out_dev,
+                           int64_t* cuts_dev, void* ws, int64_t ws_bytes, void* stream) {
     SorWs w;
-    int rc = carve_checked(ws, ws_bytes, n_local, w);
+    int rc = carve_checked(ws, ws_bytes, n_local > 0 ? n_local : 1, w);
     if (rc) return rc;
-    GSX_REQUIRE(n_global >= n_local && n_global < 2147483584ll, GSX_ERR_ARG, "sor: bad n_global");
-    return sor_dist_local_run(xyz_local_dev, n_local, idx_base, n_global, bmin_host, cell, keys_out_dev,
-                              (float4*)pos4_out_dev, w, (cudaStream_t)stream);
+    GSX_REQUIRE(n_global >= n_local && n_global >= 1 && n_global < 2147483584ll, GSX_ERR_ARG, "sor: bad n_global");
+    return sor_dist_local_run(xyz_local_dev, n_local, idx_base, n_global, world, bmin_host, cell,
+                              (float4*)pos4_out_dev, (long long*)cuts_dev, w, (cudaStream_t)stream);
 }
 
-int gsx_sor_dist_merge(const uint64_t* keys_dev, const float* pos4_dev, int64_t m, int64_t n_global,
+int gsx_sor_dist_merge(const float* pos4_dev, int64_t m, int64_t n_global, const float* bmin_host, float cell,
                        float* pos4_sorted_dev, void* ws, int64_t ws_bytes, void* stream) {
     if (m == 0) return GSX_OK;
     SorWs w;
     int rc = carve_checked(ws, ws_bytes, m, w);
     if (rc) return rc;
-    return sor_dist_merge(keys_dev, (const float4*)pos4_dev, m, n_global, (float4*)pos4_sorted_dev, w,
+    return sor_dist_merge((const float4*)pos4_dev, m, n_global, bmin_host, cell, (float4*)pos4_sorted_dev, w,
                           (cudaStream_t)stream);
+}
+
+int64_t gsx_sor_spos_offset(int64_t n) {
+    if (n < 1) return -1;
+    SorWs w = sor_carve(nullptr, 0, n, sor_sort_ws_bytes(n));
+    return (int64_t)((char*)w.spos - (char*)nullptr);
 }
 
 int gsx_sor_build_from_sorted(const float* spos4_dev, int64_t n, const float* bmin_host, float cell, void* ws,

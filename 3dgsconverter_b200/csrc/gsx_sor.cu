@@ -337,47 +337,67 @@ int sor_build(const float* xyz, int64_t n, const float* bmin, float cell, SorWs&
 // owner sorts what it received, the sorted float4 segments are all-gathered, and every rank fills its table,
 // boxes and bucket boxes from the (now identical) sorted array.  The sort work per rank drops from N to 2N/G.
 
-// stage A: keys of a local slab with hash mod n_global; payload = local index
-__global__ void __launch_bounds__(256) k_sor_keys_slab(const float* __restrict__ xyz, int64_t n, int64_t n_global,
-                                                       float bx, float by, float bz, float cell, uint64_t M64,
-                                                       uint64_t* __restrict__ keys, int32_t* __restrict__ vals) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float fx = __fdiv_rn(__fsub_rn(xyz[3 * i], bx), cell);
-    float fy = __fdiv_rn(__fsub_rn(xyz[3 * i + 1], by), cell);
-    float fz = __fdiv_rn(__fsub_rn(xyz[3 * i + 2], bz), cell);
+// hash (mod n) and in-cell Morton code of a point: shared by all key kernels
+__device__ __forceinline__ uint64_t bucket_key(float x, float y, float z, float bx, float by, float bz, float cell,
+                                               int64_t n, uint64_t M64) {
+    float fx = __fdiv_rn(__fsub_rn(x, bx), cell);
+    float fy = __fdiv_rn(__fsub_rn(y, by), cell);
+    float fz = __fdiv_rn(__fsub_rn(z, bz), cell);
     float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
     int64_t gx = (int64_t)(int32_t)flx, gy = (int64_t)(int32_t)fly, gz = (int64_t)(int32_t)flz;
     int64_t hx = (gx * 73856093LL) ^ (gy * 19349663LL) ^ (gz * 83492791LL);
     int64_t h;
     if (hx >= 0) {
         uint64_t q = __umul64hi((uint64_t)hx, M64);
-        uint64_t r = (uint64_t)hx - q * (uint64_t)n_global;
-        while (r >= (uint64_t)n_global) r -= (uint64_t)n_global;
+        uint64_t r = (uint64_t)hx - q * (uint64_t)n;
+        while (r >= (uint64_t)n) r -= (uint64_t)n;
         h = (int64_t)r;
     } else {
-        h = hx % n_global;
-        if (h < 0) h += n_global;
+        h = hx % n;
+        if (h < 0) h += n;
     }
     uint32_t sx = (uint32_t)fminf(63.f, fmaxf(0.f, (fx - flx) * 64.f));
     uint32_t sy = (uint32_t)fminf(63.f, fmaxf(0.f, (fy - fly) * 64.f));
     uint32_t sz = (uint32_t)fminf(63.f, fmaxf(0.f, (fz - flz) * 64.f));
     uint32_t mort = (spread6(sx) << 2) | (spread6(sy) << 1) | spread6(sz);
-    keys[i] = ((uint64_t)h << kMortonBits) | (uint64_t)mort;
+    return ((uint64_t)h << kMortonBits) | (uint64_t)mort;
+}
+
+// stage A: owner rank of every slab point (owner o holds the buckets [ceil(o*N/G), ceil((o+1)*N/G)))
+__global__ void __launch_bounds__(256) k_sor_owner_keys(const float* __restrict__ xyz, int64_t n, int64_t n_global,
+                                                        int world, float bx, float by, float bz, float cell,
+                                                        uint64_t M64, uint64_t* __restrict__ keys,
+                                                        int32_t* __restrict__ vals) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t h = bucket_key(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], bx, by, bz, cell, n_global, M64) >> kMortonBits;
+    // o = floor(h*G/N) satisfies ceil(o*N/G) <= h; it is the owner unless h < ceil(o*N/G) can happen -- it cannot:
+    // o*N/G <= h  =>  ceil(o*N/G) <= h because h is an integer.
+    keys[i] = (h * (uint64_t)world) / (uint64_t)n_global;
     vals[i] = (int32_t)i;
 }
 
 __global__ void __launch_bounds__(256) k_sor_gather_slab(const float* __restrict__ xyz,
-                                                         const int32_t* __restrict__ order,
-                                                         const uint64_t* __restrict__ keys_sorted, int64_t n,
-                                                         int64_t idx_base, float4* __restrict__ pos4,
-                                                         uint64_t* __restrict__ keys_out) {
+                                                         const int32_t* __restrict__ order, int64_t n,
+                                                         int64_t idx_base, float4* __restrict__ pos4) {
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     int32_t idx = order[j];
     pos4[j] = make_float4(xyz[3 * (int64_t)idx], xyz[3 * (int64_t)idx + 1], xyz[3 * (int64_t)idx + 2],
                           __int_as_float((int)(idx_base + idx)));
-    keys_out[j] = keys_sorted[j];
+}
+
+__global__ void k_sor_owner_counts(const uint64_t* __restrict__ owners_sorted, int64_t n, int world,
+                                   long long* __restrict__ cuts) {
+    // cuts[o] = first sorted position whose owner is >= o (o = 0..world); one thread per boundary, binary search
+    int o = threadIdx.x;
+    if (o > world) return;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (owners_sorted[mid] < (uint64_t)o) lo = mid + 1; else hi = mid;
+    }
+    cuts[o] = lo;
 }
 
 static int hash_bits_of(int64_t n) {
@@ -386,40 +406,53 @@ static int hash_bits_of(int64_t n) {
     return b;
 }
 
-int sor_dist_local_run(const float* xyz, int64_t n_local, int64_t idx_base, int64_t n_global, const float* bmin,
-                       float cell, uint64_t* keys_out, float4* pos4_out, SorWs& w, cudaStream_t st) {
-    if (n_local == 0) return GSX_OK;
+int sor_dist_local_run(const float* xyz, int64_t n_local, int64_t idx_base, int64_t n_global, int world,
+                       const float* bmin, float cell, float4* pos4_out, long long* cuts_dev, SorWs& w,
+                       cudaStream_t st) {
+    GSX_REQUIRE(world >= 1 && world <= 255, GSX_ERR_ARG, "sor: world size must be in [1,255]");
+    if (n_local == 0) {
+        GSX_CUDA_CHECK(cudaMemsetAsync(cuts_dev, 0, (size_t)(world + 1) * sizeof(long long), st));
+        return GSX_OK;
+    }
     int blocks = (int)((n_local + 255) / 256);
-    k_sor_keys_slab<<<blocks, 256, 0, st>>>(xyz, n_local, n_global, bmin[0], bmin[1], bmin[2], cell,
-                                            0xFFFFFFFFFFFFFFFFull / (uint64_t)n_global, w.keys0, w.vals0);
+    k_sor_owner_keys<<<blocks, 256, 0, st>>>(xyz, n_local, n_global, world, bmin[0], bmin[1], bmin[2], cell,
+                                             0xFFFFFFFFFFFFFFFFull / (uint64_t)n_global, w.keys0, w.vals0);
     GSX_KERNEL_CHECK();
     uint64_t* ks = nullptr;
     int32_t* order = nullptr;
-    int rc = radix_sort_pairs(w.keys0, w.keys1, w.vals0, w.vals1, n_local, 0, kMortonBits + hash_bits_of(n_global),
-                              w.sort_ws, w.sort_ws_bytes, &ks, &order, st);
+    int rc = radix_sort_pairs(w.keys0, w.keys1, w.vals0, w.vals1, n_local, 0, 8, w.sort_ws, w.sort_ws_bytes, &ks,
+                              &order, st);  // one stable pass: a partition by owner
     if (rc) return rc;
-    k_sor_gather_slab<<<blocks, 256, 0, st>>>(xyz, order, ks, n_local, idx_base, pos4_out, keys_out);
+    k_sor_gather_slab<<<blocks, 256, 0, st>>>(xyz, order, n_local, idx_base, pos4_out);
+    GSX_KERNEL_CHECK();
+    k_sor_owner_counts<<<1, 256, 0, st>>>(ks, n_local, world, cuts_dev);
     GSX_KERNEL_CHECK();
     return GSX_OK;
 }
 
 // stage B: order the received runs of this rank's bucket range
-__global__ void __launch_bounds__(256) k_iota(int32_t* __restrict__ v, int64_t n) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) v[i] = (int32_t)i;
-}
 __global__ void __launch_bounds__(256) k_gather4(const float4* __restrict__ in, const int32_t* __restrict__ order,
                                                  int64_t n, float4* __restrict__ out) {
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j < n) out[j] = in[order[j]];
 }
 
-int sor_dist_merge(const uint64_t* keys_in, const float4* pos4_in, int64_t m, int64_t n_global, float4* pos4_out,
+__global__ void __launch_bounds__(256) k_sor_keys_pos4(const float4* __restrict__ pos4, int64_t n, int64_t n_global,
+                                                       float bx, float by, float bz, float cell, uint64_t M64,
+                                                       uint64_t* __restrict__ keys, int32_t* __restrict__ vals) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = pos4[i];
+    keys[i] = bucket_key(p.x, p.y, p.z, bx, by, bz, cell, n_global, M64);
+    vals[i] = (int32_t)i;
+}
+
+int sor_dist_merge(const float4* pos4_in, int64_t m, int64_t n_global, const float* bmin, float cell, float4* pos4_out,
                    SorWs& w, cudaStream_t st) {
     if (m == 0) return GSX_OK;
     int blocks = (int)((m + 255) / 256);
-    GSX_CUDA_CHECK(cudaMemcpyAsync(w.keys0, keys_in, (size_t)m * 8, cudaMemcpyDeviceToDevice, st));
-    k_iota<<<blocks, 256, 0, st>>>(w.vals0, m);
+    k_sor_keys_pos4<<<blocks, 256, 0, st>>>(pos4_in, m, n_global, bmin[0], bmin[1], bmin[2], cell,
+                                            0xFFFFFFFFFFFFFFFFull / (uint64_t)n_global, w.keys0, w.vals0);
     GSX_KERNEL_CHECK();
     uint64_t* ks = nullptr;
     int32_t* order = nullptr;
@@ -438,20 +471,7 @@ __global__ void __launch_bounds__(256) k_sor_keys_sorted(const float4* __restric
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 p = spos[i];
-    int64_t gx = (int64_t)(int32_t)floorf(__fdiv_rn(__fsub_rn(p.x, bx), cell));
-    int64_t gy = (int64_t)(int32_t)floorf(__fdiv_rn(__fsub_rn(p.y, by), cell));
-    int64_t gz = (int64_t)(int32_t)floorf(__fdiv_rn(__fsub_rn(p.z, bz), cell));
-    int64_t hx = (gx * 73856093LL) ^ (gy * 19349663LL) ^ (gz * 83492791LL);
-    int64_t h;
-    if (hx >= 0) {
-        uint64_t q = __umul64hi((uint64_t)hx, M64);
-        uint64_t r = (uint64_t)hx - q * (uint64_t)n;
-        while (r >= (uint64_t)n) r -= (uint64_t)n;
-        h = (int64_t)r;
-    } else {
-        h = hx % n;
-        if (h < 0) h += n;
-    }
+    uint64_t h = bucket_key(p.x, p.y, p.z, bx, by, bz, cell, n, M64) >> kMortonBits;
     keys[i] = (uint64_t)h << kMortonBits;
 }
 

@@ -36,9 +36,10 @@ int sor_build(const float* xyz, int64_t n, const float* bmin, float cell, SorWs&
 int sor_mean_dists(SorWs& w, int64_t q_begin, int64_t q_end, int k, int hash_mode, const float* bmin, float cell,
                    float* final_means, unsigned long long* stats, cudaStream_t st);
 
-int sor_dist_local_run(const float* xyz, int64_t n_local, int64_t idx_base, int64_t n_global, const float* bmin,
-                       float cell, uint64_t* keys_out, float4* pos4_out, SorWs& w, cudaStream_t st);
-int sor_dist_merge(const uint64_t* keys_in, const float4* pos4_in, int64_t m, int64_t n_global, float4* pos4_out,
+int sor_dist_local_run(const float* xyz, int64_t n_local, int64_t idx_base, int64_t n_global, int world,
+                       const float* bmin, float cell, float4* pos4_out, long long* cuts_dev, SorWs& w,
+                       cudaStream_t st);
+int sor_dist_merge(const float4* pos4_in, int64_t m, int64_t n_global, const float* bmin, float cell, float4* pos4_out,
                    SorWs& w, cudaStream_t st);
 int sor_build_from_sorted(const float4* spos_in, int64_t n, const float* bmin, float cell, SorWs& w, cudaStream_t st);
 

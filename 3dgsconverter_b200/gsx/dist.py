@@ -187,34 +187,47 @@ def build_grid_distributed(xyz_local: torch.Tensor, group=None):
     cell = float(lib.gsx_sor_cell_size(mm.ctypes.data_as(C.POINTER(C.c_float)), n_global))
     bmin = mm[:3].copy()
     bminp = bmin.ctypes.data_as(C.POINTER(C.c_float))
-    # A. local sorted run
+    # A. stable partition of the slab by bucket owner (one radix pass) + float4 gather
     ws_l = sor.workspace(max(n_local, 1), dev)
-    keys = torch.empty(n_local, dtype=torch.int64, device=dev)
     pos4 = torch.empty((n_local, 4), dtype=torch.float32, device=dev)
-    check(lib.gsx_sor_dist_local_run(_ptr(xyz_local), n_local, idx_base, n_global, bminp, cell, _ptr(keys), _ptr(pos4),
-                                     _ptr(ws_l), ws_l.numel(), _stream()), "gsx_sor_dist_local_run")
-    # split by owner (keys are sorted; owner boundaries are monotone in the key)
-    bounds = torch.tensor([b << 18 for b in _owner_bounds(n_global, world)], dtype=torch.int64, device=dev)
-    cut = torch.searchsorted(keys, bounds)          # [world+1] positions
-    send = (cut[1:] - cut[:-1]).to(torch.int64)
+    cuts = torch.zeros(world + 1, dtype=torch.int64, device=dev)
+    check(lib.gsx_sor_dist_local_run(_ptr(xyz_local), n_local, idx_base, n_global, world, bminp, cell, _ptr(pos4),
+                                     _ptr(cuts), _ptr(ws_l), ws_l.numel(), _stream()), "gsx_sor_dist_local_run")
+    send = (cuts[1:] - cuts[:-1]).contiguous()
     recv = torch.empty_like(send)
     dist.all_to_all_single(recv, send, group=group)
-    send_l, recv_l = [int(v) for v in send.tolist()], [int(v) for v in recv.tolist()]
+    both = torch.stack([send, recv]).tolist()      # one host sync for both split lists
+    send_l, recv_l = [int(v) for v in both[0]], [int(v) for v in both[1]]
     m = sum(recv_l)
-    keys_r = torch.empty(m, dtype=torch.int64, device=dev)
     pos4_r = torch.empty((m, 4), dtype=torch.float32, device=dev)
-    dist.all_to_all_single(keys_r, keys, recv_l, send_l, group=group)
     dist.all_to_all_single(pos4_r, pos4, recv_l, send_l, group=group)
-    # B. owner-local ordering of the received runs
-    seg = torch.empty((m, 4), dtype=torch.float32, device=dev)
+    # B. owner-local sort of the received points by (bucket, in-cell Morton)
     ws_m = ws_l if m <= n_local else sor.workspace(max(m, 1), dev)
-    check(lib.gsx_sor_dist_merge(_ptr(keys_r), _ptr(pos4_r), m, n_global, _ptr(seg), _ptr(ws_m), ws_m.numel(),
-                                 _stream()), "gsx_sor_dist_merge")
-    # all-gather of the sorted segments in owner order = the globally sorted array
-    spos_full, seg_sizes = _all_gather_rows(seg, group)
-    assert spos_full.shape[0] == n_global
-    # C. table, boxes, bucket boxes -- replicated, linear in n_global
     ws = sor.workspace(n_global, dev)
+    seg_sizes_t = torch.zeros(world, dtype=torch.int64, device=dev)
+    seg_sizes_t[rank] = m
+    dist.all_reduce(seg_sizes_t, group=group)
+    seg_sizes = [int(v) for v in seg_sizes_t.tolist()]
+    off = lib.gsx_sor_spos_offset(n_global)
+    spos_full = ws[off: off + n_global * 16].view(torch.float32).view(n_global, 4)   # all-gather target in ws
+    if len(set(seg_sizes)) == 1:
+        seg = torch.empty((m, 4), dtype=torch.float32, device=dev)
+        check(lib.gsx_sor_dist_merge(_ptr(pos4_r), m, n_global, bminp, cell, _ptr(seg), _ptr(ws_m), ws_m.numel(),
+                                     _stream()), "gsx_sor_dist_merge")
+        dist.all_gather_into_tensor(spos_full, seg, group=group)
+    else:
+        # ragged owners: every rank writes its segment at its global offset, the rest is zero -> all-reduce? no:
+        # broadcast segment by segment (sizes differ by at most a few buckets' worth of points)
+        base = sum(seg_sizes[:rank])
+        seg = spos_full[base: base + m]
+        check(lib.gsx_sor_dist_merge(_ptr(pos4_r), m, n_global, bminp, cell, _ptr(seg), _ptr(ws_m), ws_m.numel(),
+                                     _stream()), "gsx_sor_dist_merge")
+        o = 0
+        for r, sz in enumerate(seg_sizes):
+            if sz:
+                dist.broadcast(spos_full[o: o + sz], src=dist.get_global_rank(group, r) if group else r, group=group)
+            o += sz
+    # C. table, boxes, bucket boxes -- replicated, linear in n_global
     check(lib.gsx_sor_build_from_sorted(_ptr(spos_full), n_global, bminp, cell, _ptr(ws), ws.numel(), _stream()),
           "gsx_sor_build_from_sorted")
     return sor.SorGrid(n_global, ws, bmin, cell), sizes

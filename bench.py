@@ -192,6 +192,18 @@ def main():
             sor.mean_dists(grid, K_SOR, args.hash, out=means)
             e2.record()
             mask = sor.threshold_mask(means, sor.mean_std(means), SIGMA)
+        elif os.environ.get("GSX_DIST_BUILD", "1") == "1":
+            # distributed grid build: local sort by global bucket key -> all-to-all by bucket owner -> owner sort
+            # -> all-gather of the sorted float4 segments -> table/boxes filled locally (gsx/dist.py)
+            e0.record()
+            grid, sizes = gd.build_grid_distributed(xyz)
+            e1.record()
+            qb, qe = gd.query_range(n_total, rank, world)
+            means.zero_()
+            sor.mean_dists(grid, K_SOR, args.hash, out=means, q_range=(qb, qe))
+            e2.record()
+            dist.all_reduce(means)
+            mask = sor.threshold_mask(means, sor.mean_std(means), SIGMA)[rank * n:(rank + 1) * n]
         else:
             xyz_all, sizes = gd._all_gather_rows(xyz)
             e0.record()
@@ -246,7 +258,7 @@ def main():
     # B = queries*(16 own float4 + 27*32 bucket entries {start,end,box} + 4 result) + 16*candidates scanned
     #     + 32*chunk/super boxes tested,
     # counted exactly by the instrumented build of the same kernel.
-    grid = sor.build_grid(xyz if world == 1 else gd._all_gather_rows(xyz)[0], ws)
+    grid = sor.build_grid(xyz, ws) if world == 1 else gd.build_grid_distributed(xyz)[0]
     qr = gd.query_range(n_total, rank, world)
     _, st = sor.mean_dists(grid, K_SOR, args.hash, out=means, want_stats=True, q_range=qr)
     alg_bytes = st["queries"] * (16 + 27 * 32 + 4) + 16 * st["scanned"] + 32 * st["box_tests"]
@@ -287,8 +299,11 @@ def main():
                                f"cloud of {n_total} splats",
                    "splats_per_gpu": n, "k": K_SOR, "sigma": SIGMA, "hash_mode": args.hash,
                    "l2": "256 MiB flush write before every step + working set (~0.6 GB/step) larger than L2",
-                   "kept": kept, "parallelism": f"dp{world}: all-gather xyz, replicated grid, sharded queries, "
-                                                "one all-reduce" if world > 1 else "single GPU"},
+                   "kept": kept, "parallelism": (f"dp{world}: distributed grid build (all-to-all by bucket owner + "
+                                                 "all-gather of sorted float4), sharded queries, one all-reduce"
+                                                 if os.environ.get("GSX_DIST_BUILD", "1") == "1" else
+                                                 f"dp{world}: all-gather xyz, replicated grid, sharded queries, "
+                                                 "one all-reduce") if world > 1 else "single GPU"},
         "stage_ms": {"build": round(float(np.mean(build_ms)), 3), "knn": round(knn_avg_ms, 3)},
         "gpu_launches": int(launches), "roofline": roofline,
     }
@@ -348,7 +363,8 @@ def measure_e2e_sharded(xyz_np, args, dev, rank, world):
 
     def once():
         x = pinned.to(dev, non_blocking=True)
-        mask = gd.sor_filter_sharded(x, K_SOR, SIGMA, args.hash)
+        mask = (gd.sor_filter_sharded_v2 if os.environ.get("GSX_DIST_BUILD", "1") == "1"
+                else gd.sor_filter_sharded)(x, K_SOR, SIGMA, args.hash)
         out.copy_(mask, non_blocking=True)
         torch.cuda.synchronize()
     once()

@@ -61,18 +61,21 @@ int gsx_sor_build(const float* xyz_dev, int64_t n, const float* bmin_host, float
 /* Distributed form of gsx_sor_build for a cloud sharded over G processes (one per GPU); the collectives
  * between the stages are the caller's (gsx/dist.py uses NCCL).  Bucket-range ownership: rank o owns the
  * buckets [ceil(o*n_global/G), ceil((o+1)*n_global/G)).
- *  A. local_run:  key = (hash mod n_global) << 18 | Morton of every slab point, sorted; outputs the sorted keys
- *     and float4 {x,y,z, bits(idx_base + local index)} -> the caller splits them by owner (all-to-all).
- *  B. merge:      orders the m received pairs of this rank's bucket range -> sorted float4 segment
- *     -> the caller all-gathers the segments in owner order = the globally sorted array.
+ *  A. local_run:  stable partition of the slab by bucket owner (one radix pass); outputs float4
+ *     {x,y,z, bits(idx_base + local index)} grouped by owner and cuts_dev[G+1] = first position of every owner
+ *     -> the caller exchanges the groups (all-to-all).
+ *  B. merge:      sorts the m received points of this rank's bucket range by (bucket, in-cell Morton)
+ *     -> the caller all-gathers the segments in owner order = the globally hash-sorted array.
  *  C. build_from_sorted: table, bucket boxes and chunk/super boxes from that array (what gsx_sor_build
- *     leaves in the workspace), after which gsx_sor_mean_dists[_range] can run.
+ *     leaves in the workspace), after which gsx_sor_mean_dists[_range] can run.  If spos4_dev already points at
+ *     ws + gsx_sor_spos_offset(n) (all-gather straight into the workspace) no copy is made.
  * ws of A and B: gsx_sor_workspace_bytes(n_local) resp. (m); of C: gsx_sor_workspace_bytes(n_global). */
 int gsx_sor_dist_local_run(const float* xyz_local_dev, int64_t n_local, int64_t idx_base, int64_t n_global,
-                           const float* bmin_host, float cell, uint64_t* keys_out_dev, float* pos4_out_dev, void* ws,
-                           int64_t ws_bytes, void* stream);
-int gsx_sor_dist_merge(const uint64_t* keys_dev, const float* pos4_dev, int64_t m, int64_t n_global,
+                           int32_t world, const float* bmin_host, float cell, float* pos4_out_dev,
+                           int64_t* cuts_dev, void* ws, int64_t ws_bytes, void* stream);
+int gsx_sor_dist_merge(const float* pos4_dev, int64_t m, int64_t n_global, const float* bmin_host, float cell,
                        float* pos4_sorted_dev, void* ws, int64_t ws_bytes, void* stream);
+int64_t gsx_sor_spos_offset(int64_t n);
 int gsx_sor_build_from_sorted(const float* spos4_dev, int64_t n, const float* bmin_host, float cell, void* ws,
                               int64_t ws_bytes, void* stream);
 

@@ -94,8 +94,9 @@ def test_mean_std_matches_numpy(cuda, gsx_lib):
 
 
 def test_build_from_sorted_equals_build(cuda, gsx_lib):
-    """Stage C of the distributed build on one GPU: local run -> merge -> build_from_sorted must give the
-    same mean distances as the one-shot build (world size 1 degenerates to exactly this)."""
+    """The stages of the distributed build on one GPU: partition by owner (3 pretend owners) -> per-owner sort
+    -> concatenation in owner order -> build_from_sorted must give the same mean distances as the one-shot
+    build (and as the oracle)."""
     import ctypes as C
     import torch
     import oracle
@@ -107,20 +108,24 @@ def test_build_from_sorted_equals_build(cuda, gsx_lib):
     n = xyz.shape[0]
     ref = sor.build_grid(xyz)
     bminp = ref.bmin.ctypes.data_as(C.POINTER(C.c_float))
+    world = 3
     ws = sor.workspace(n, cuda)
-    keys = torch.empty(n, dtype=torch.int64, device=cuda)
     pos4 = torch.empty((n, 4), dtype=torch.float32, device=cuda)
-    check(lib.gsx_sor_dist_local_run(_ptr(xyz), n, 0, n, bminp, ref.cell, _ptr(keys), _ptr(pos4), _ptr(ws), ws.numel(),
-                                     _stream()))
-    assert bool((keys[1:] >= keys[:-1]).all())
-    # split in two "source ranks" and merge them back (exercises stage B)
-    half = n // 2
-    perm_keys = torch.cat([keys[half:], keys[:half]])
-    perm_pos = torch.cat([pos4[half:], pos4[:half]])
-    seg = torch.empty_like(pos4)
-    check(lib.gsx_sor_dist_merge(_ptr(perm_keys), _ptr(perm_pos), n, n, _ptr(seg), _ptr(ws), ws.numel(), _stream()))
+    cuts = torch.zeros(world + 1, dtype=torch.int64, device=cuda)
+    check(lib.gsx_sor_dist_local_run(_ptr(xyz), n, 0, n, world, bminp, ref.cell, _ptr(pos4), _ptr(cuts), _ptr(ws),
+                                     ws.numel(), _stream()))
+    c = cuts.tolist()
+    assert c[0] == 0 and c[-1] == n and all(c[i] <= c[i + 1] for i in range(world))
+    assert sorted(pos4[:, 3].view(torch.int32).tolist()) == list(range(n))      # a permutation of the slab
     ws2 = sor.workspace(n, cuda)
-    check(lib.gsx_sor_build_from_sorted(_ptr(seg), n, bminp, ref.cell, _ptr(ws2), ws2.numel(), _stream()))
+    off = lib.gsx_sor_spos_offset(n)
+    spos_full = ws2[off: off + n * 16].view(torch.float32).view(n, 4)
+    for o in range(world):                                                     # "owner o" sorts its range
+        m = c[o + 1] - c[o]
+        seg_in = pos4[c[o]: c[o + 1]].contiguous()
+        check(lib.gsx_sor_dist_merge(_ptr(seg_in), m, n, bminp, ref.cell, _ptr(spos_full[c[o]: c[o + 1]]), _ptr(ws),
+                                     ws.numel(), _stream()))
+    check(lib.gsx_sor_build_from_sorted(_ptr(spos_full), n, bminp, ref.cell, _ptr(ws2), ws2.numel(), _stream()))
     grid2 = sor.SorGrid(n, ws2, ref.bmin, ref.cell)
     for mode in ("i32wrap", "i64"):
         a = sor.mean_dists(ref, 16, mode).cpu().numpy()
