@@ -233,6 +233,12 @@ def build_grid_distributed(xyz_local: torch.Tensor, group=None):
     return sor.SorGrid(n_global, ws, bmin, cell), sizes
 
 
+def sor_filter_auto(xyz_local, k=25, threshold_factor=1.0, hash_mode=None, group=None, return_means=False):
+    """Picks the grid-build strategy by world size (replicated up to 3 ranks, distributed from 4)."""
+    f = sor_filter_sharded_v2 if dist.get_world_size(group) >= 4 else sor_filter_sharded
+    return f(xyz_local, k, threshold_factor, hash_mode, group=group, return_means=return_means)
+
+
 def sor_filter_sharded_v2(xyz_local: torch.Tensor, k: int = 25, threshold_factor: float = 1.0,
                           hash_mode: str | None = None, group=None, return_means: bool = False):
     """Like sor_filter_sharded, with the distributed grid build (no replicated sort, no all-gather of raw xyz)."""

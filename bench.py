@@ -192,7 +192,7 @@ def main():
             sor.mean_dists(grid, K_SOR, args.hash, out=means)
             e2.record()
             mask = sor.threshold_mask(means, sor.mean_std(means), SIGMA)
-        elif os.environ.get("GSX_DIST_BUILD", "1") == "1":
+        elif use_dist_build:
             # distributed grid build: local sort by global bucket key -> all-to-all by bucket owner -> owner sort
             # -> all-gather of the sorted float4 segments -> table/boxes filled locally (gsx/dist.py)
             e0.record()
@@ -220,6 +220,11 @@ def main():
         return mask
 
     step.events = []
+    # replicated grid build (all-gather raw xyz, every rank sorts the union cloud) is faster up to 2-3 ranks;
+    # from 4 ranks on the distributed build wins (measured: N=2 3.1 vs 3.9 ms, N=4 6.1 vs 5.1 ms).  Both are
+    # bit-identical to the single-GPU filter (tests/test_multigpu_nccl.py).
+    env_db = os.environ.get("GSX_DIST_BUILD", "auto")
+    use_dist_build = world >= 4 if env_db == "auto" else env_db == "1"
 
     def barrier():
         if world > 1:
@@ -258,7 +263,7 @@ def main():
     # B = queries*(16 own float4 + 27*32 bucket entries {start,end,box} + 4 result) + 16*candidates scanned
     #     + 32*chunk/super boxes tested,
     # counted exactly by the instrumented build of the same kernel.
-    grid = sor.build_grid(xyz, ws) if world == 1 else gd.build_grid_distributed(xyz)[0]
+    grid = sor.build_grid(xyz, ws) if world == 1 else gd.build_grid_distributed(xyz)[0]  # same grid either way
     qr = gd.query_range(n_total, rank, world)
     _, st = sor.mean_dists(grid, K_SOR, args.hash, out=means, want_stats=True, q_range=qr)
     alg_bytes = st["queries"] * (16 + 27 * 32 + 4) + 16 * st["scanned"] + 32 * st["box_tests"]
@@ -301,7 +306,7 @@ def main():
                    "l2": "256 MiB flush write before every step + working set (~0.6 GB/step) larger than L2",
                    "kept": kept, "parallelism": (f"dp{world}: distributed grid build (all-to-all by bucket owner + "
                                                  "all-gather of sorted float4), sharded queries, one all-reduce"
-                                                 if os.environ.get("GSX_DIST_BUILD", "1") == "1" else
+                                                 if use_dist_build else
                                                  f"dp{world}: all-gather xyz, replicated grid, sharded queries, "
                                                  "one all-reduce") if world > 1 else "single GPU"},
         "stage_ms": {"build": round(float(np.mean(build_ms)), 3), "knn": round(knn_avg_ms, 3)},
@@ -363,8 +368,9 @@ def measure_e2e_sharded(xyz_np, args, dev, rank, world):
 
     def once():
         x = pinned.to(dev, non_blocking=True)
-        mask = (gd.sor_filter_sharded_v2 if os.environ.get("GSX_DIST_BUILD", "1") == "1"
-                else gd.sor_filter_sharded)(x, K_SOR, SIGMA, args.hash)
+        env_db = os.environ.get("GSX_DIST_BUILD", "auto")
+        dist_build = world >= 4 if env_db == "auto" else env_db == "1"
+        mask = (gd.sor_filter_sharded_v2 if dist_build else gd.sor_filter_sharded)(x, K_SOR, SIGMA, args.hash)
         out.copy_(mask, non_blocking=True)
         torch.cuda.synchronize()
     once()

@@ -45,10 +45,10 @@ def _worker(rank, world, port, n_per, q):
 def test_sharded_equals_single_gpu(gsx_lib):
     import torch
     import torch.multiprocessing as mp
-    world = min(torch.cuda.device_count(), 4)
+    world = min(torch.cuda.device_count(), 2)   # 2 ranks exercise every collective; keeps GPU time low
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
-    n_per = 400_000
+    n_per = 300_000
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 33500 + (os.getpid() % 2000)
