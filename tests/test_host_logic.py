@@ -1,0 +1,108 @@
+"""CPU: host-side logic of the product (no GPU): cluster selection, slider maps, owner partition, bench
+reference arm.  Anything numeric is checked against the oracle / the reference's formulas."""
+import json
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _cloud_for_voxels(vox, counts, voxel):
+    pts = []
+    for v, c in zip(vox, counts):
+        pts.append(np.tile((np.asarray(v) + 0.5) * voxel, (c, 1)))
+    return np.concatenate(pts).astype(np.float32)
+
+
+@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("multi", [False, True])
+def test_select_clusters_matches_reference_order(gsx_lib, seed, multi):
+    """6-connected components + 'largest / >= 5 % of largest' incl. ties between equally large clusters
+    (decided by Python set iteration order): gsx.density.select_clusters vs the oracle's BFS."""
+    from gsx import density
+    rng = np.random.default_rng(seed)
+    # a few blobs of voxels, several with the same size so that ties occur
+    vox = set()
+    for _ in range(6):
+        c = rng.integers(-6, 6, 3)
+        for _ in range(int(rng.integers(1, 4))):
+            c = c + rng.integers(-1, 2, 3) * (rng.random(3) < 0.5)
+            vox.add(tuple(int(x) for x in c))
+    vox = np.array(sorted(vox), dtype=np.int64)
+    counts = np.full(len(vox), 5)
+    voxel = 1.0
+    pts = _cloud_for_voxels(vox, counts, voxel)
+    thr_pct = 100.0 * 5 / len(pts) * 0.999          # min_points = int(n * thr/100) = 4 -> every voxel dense
+    want_mask, info = oracle.density_mask(pts, voxel, thr_pct, None, multi)
+    kept, n_kept, max_len = density.select_clusters(vox, multi)      # vox is already lexicographically sorted
+    kept_set = set(map(tuple, kept))
+    q = np.floor(pts / np.float32(voxel)).astype(np.int64)
+    got_mask = np.array([tuple(v) in kept_set for v in q])
+    assert n_kept == info["clusters"] and max_len == info["max_len"]
+    assert np.array_equal(got_mask, want_mask)
+
+
+def test_sliders_match_reference_formulas(gsx_lib):
+    from gsx import density
+    for s in (0.0, 0.1, 0.5, 0.9, 1.0, 1.5):
+        assert density.slider(s) == oracle.density_slider(s) == (max(0.1, 2.0 - s * 1.8), 0.1 + s * 0.9)
+
+
+def test_owner_partition_formula(gsx_lib):
+    """Bucket-range ownership of the distributed build: floor(h*G/N) is the owner whose range
+    [ceil(o*N/G), ceil((o+1)*N/G)) contains h, the ranges tile [0,N) and are balanced."""
+    from gsx.dist import _owner_bounds
+    rng = np.random.default_rng(0)
+    for n in (1, 7, 1000, 10_000_019, 2_000_000_000):
+        for g in (1, 2, 3, 4, 8):
+            b = _owner_bounds(n, g)
+            assert b[0] == 0 and b[-1] == n and all(b[i] <= b[i + 1] for i in range(g))
+            assert max(b[i + 1] - b[i] for i in range(g)) - min(b[i + 1] - b[i] for i in range(g)) <= 1
+            hs = np.unique(np.r_[rng.integers(0, n, 200), [0, n - 1], np.array(b[:-1]), np.maximum(np.array(b[1:]) - 1, 0)])
+            for h in hs[hs < n]:
+                o = int(h) * g // n
+                assert b[o] <= h < b[o + 1], (n, g, h, o)
+
+
+def test_bench_reference_arm_line():
+    """`bench.py --impl reference` prints one JSON line with the contract's keys (tiny sample, CPU only)."""
+    out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-sample", "20000", "--n", "20000"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "Msplats/s" and line["value"] > 0
+    for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "config", "e2e",
+                "cpu_baseline"):
+        assert key in line
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_dropin_mirror_has_reference_surface():
+    """Names and signatures of the plugin surface -- importable without a GPU."""
+    import inspect
+    from gsconverter.processing import DataProcessor, gpu_ops
+    sig = lambda f: list(inspect.signature(f).parameters)  # noqa: E731
+    assert sig(gpu_ops.kmeans) == ["data", "k", "max_iter", "tolerance", "use_gpu", "verbose"]
+    assert sig(gpu_ops.filter_sor_gpu) == ["data_np", "k", "threshold_factor", "verbose"]
+    assert sig(DataProcessor.apply_density_filter) == ["self", "voxel_size", "threshold_percentage", "sensitivity",
+                                                       "keep_multicluster"]
+    assert sig(DataProcessor.remove_flyers) == ["self", "k", "threshold_factor", "chunk_size", "intensity"]
+    assert sig(DataProcessor.crop_by_bbox) == ["self", "min_x", "min_y", "min_z", "max_x", "max_y", "max_z"]
+    assert sig(DataProcessor.apply_alpha_filter) == ["self", "min_opacity_u8"]
+    assert isinstance(gpu_ops.HAS_TAICHI, bool)
+    d = inspect.signature(gpu_ops.kmeans).parameters
+    assert d["max_iter"].default == 10 and d["tolerance"].default == 1e-4 and d["use_gpu"].default is True
+    d = inspect.signature(DataProcessor.remove_flyers).parameters
+    assert d["k"].default == 25 and d["threshold_factor"].default == 10.5 and d["chunk_size"].default == 50000
+    # k >= N passthrough and the explicit CPU request work without a GPU (gpu_ops.py:30-38)
+    X = np.arange(12, dtype=np.float32).reshape(4, 3)
+    C, L = gpu_ops.kmeans(X, 9)
+    assert np.array_equal(C, X) and np.array_equal(L, np.arange(4, dtype=np.int32))
+    C, L = gpu_ops.kmeans(np.random.default_rng(0).random((200, 3)).astype(np.float32), 4, use_gpu=False)
+    assert C.shape == (4, 3) and L.shape == (200,)
