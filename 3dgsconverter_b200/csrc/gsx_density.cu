@@ -83,6 +83,63 @@ __global__ void __launch_bounds__(256) k_vox_count_grid(const float* __restrict_
     }
 }
 
+// Same histogram with per-block aggregation: clustered clouds put 10^5..10^6 points into a handful of voxels and
+// same-address global atomics serialise in L2.  Each block first counts its 2048 points in a 1024-slot shared-memory
+// hash (cell index -> count) and then issues ONE global atomicAdd per distinct cell; the increment may be > 1, so the
+// threshold crossing is detected as old < thr <= old + c (still exactly one block sees it).
+constexpr int kAggItems = 8, kAggSlots = 1024;
+__global__ void __launch_bounds__(256) k_vox_count_grid_agg(const float* __restrict__ xyz, int64_t n, float voxel,
+                                                            VoxGrid g, int thr, int* __restrict__ grid,
+                                                            unsigned long long* __restrict__ counters,
+                                                            long long* __restrict__ dense_vox, int64_t cap) {
+    __shared__ unsigned int skey[kAggSlots];
+    __shared__ int sval[kAggSlots];
+    for (int t = threadIdx.x; t < kAggSlots; t += 256) {
+        skey[t] = 0xffffffffu;
+        sval[t] = 0;
+    }
+    __syncthreads();
+    const int64_t base = (int64_t)blockIdx.x * (256 * kAggItems);
+    auto commit = [&](unsigned int idx, int c) {
+        int old = atomicAdd(grid + idx, c);
+        if (old == 0) atomicAdd(counters + 1, 1ull);
+        if (old < thr && old + c >= thr) {
+            unsigned long long slot = atomicAdd(counters, 1ull);
+            if ((int64_t)slot < cap) {
+                size_t cz = idx % (size_t)g.dim[2], cy = (idx / (size_t)g.dim[2]) % (size_t)g.dim[1],
+                       cx = idx / ((size_t)g.dim[2] * (size_t)g.dim[1]);
+                dense_vox[3 * slot] = (long long)cx + g.q0[0];
+                dense_vox[3 * slot + 1] = (long long)cy + g.q0[1];
+                dense_vox[3 * slot + 2] = (long long)cz + g.q0[2];
+            }
+        }
+    };
+#pragma unroll 2
+    for (int e = 0; e < kAggItems; ++e) {
+        const int64_t i = base + (int64_t)e * 256 + threadIdx.x;
+        if (i >= n) break;
+        long long qx = voxel_of(xyz[3 * i], voxel), qy = voxel_of(xyz[3 * i + 1], voxel),
+                  qz = voxel_of(xyz[3 * i + 2], voxel);
+        const unsigned int idx =
+            (unsigned int)(((size_t)(qx - g.q0[0]) * g.dim[1] + (size_t)(qy - g.q0[1])) * g.dim[2] + (size_t)(qz - g.q0[2]));
+        unsigned int slot = (idx * 2654435761u) >> 22;  // 10 bits
+        bool placed = false;
+#pragma unroll 1
+        for (int probe = 0; probe < 8 && !placed; ++probe) {
+            unsigned int cur = atomicCAS(&skey[slot], 0xffffffffu, idx);
+            if (cur == 0xffffffffu || cur == idx) {
+                atomicAdd(&sval[slot], 1);
+                placed = true;
+            }
+            slot = (slot + 1) & (kAggSlots - 1);
+        }
+        if (!placed) commit(idx, 1);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < kAggSlots; t += 256)
+        if (sval[t] > 0) commit(skey[t], sval[t]);
+}
+
 __global__ void k_vox_dense_counts_grid(const long long* __restrict__ dense_vox, int64_t nd, VoxGrid g,
                                         const int* __restrict__ grid, int* __restrict__ dense_cnt) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -186,7 +243,12 @@ int density_voxel_count(const float* xyz, int64_t n, float voxel, int64_t min_po
     if (use_grid) {
         size_t ncell = (size_t)g.dim[0] * g.dim[1] * g.dim[2];
         GSX_CUDA_CHECK(cudaMemsetAsync(blob, 0, ncell * 4, st));
-        k_vox_count_grid<<<blocks, 256, 0, st>>>(xyz, n, voxel, g, thr, (int*)blob, counters, dvox, cap);
+        if (ncell < 0xfffffff0ull) {
+            int ablocks = (int)((n + 256 * kAggItems - 1) / (256 * kAggItems));
+            k_vox_count_grid_agg<<<ablocks, 256, 0, st>>>(xyz, n, voxel, g, thr, (int*)blob, counters, dvox, cap);
+        } else {
+            k_vox_count_grid<<<blocks, 256, 0, st>>>(xyz, n, voxel, g, thr, (int*)blob, counters, dvox, cap);
+        }
     } else {
         size_t slots = 64;
         while (slots < (size_t)2 * n) slots <<= 1;
@@ -325,29 +387,44 @@ int density_grid_dense(const int* grid_dev, const int64_t* q0, const int64_t* di
 }
 
 // ---------------------------------------------------------------- membership mask
-__global__ void __launch_bounds__(256) k_vox_member(const float* __restrict__ xyz, int64_t n, float voxel,
-                                                    long long ox, long long oy, long long oz,
+__device__ __forceinline__ uint8_t vox_member_one(float x, float y, float z, float voxel, long long ox,
+                                                  long long oy, long long oz,
+                                                  const unsigned long long* __restrict__ set, uint64_t slot_mask) {
+    long long rx = voxel_of(x, voxel) - ox, ry = voxel_of(y, voxel) - oy, rz = voxel_of(z, voxel) - oz;
+    if (rx < 0 || ry < 0 || rz < 0 || rx >= kAxisLim || ry >= kAxisLim || rz >= kAxisLim) return 0;
+    uint64_t key = pack_rel(rx, ry, rz);
+    uint64_t s = mix64(key) & slot_mask;
+    for (;;) {
+        unsigned long long cur = __ldg(set + s);
+        if (cur == key) return 1;
+        if (cur == 0ull) return 0;
+        s = (s + 1) & slot_mask;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_vox_member(const float* __restrict__ xyz, int64_t begin, int64_t n,
+                                                    float voxel, long long ox, long long oy, long long oz,
                                                     const unsigned long long* __restrict__ set, uint64_t slot_mask,
                                                     uint8_t* __restrict__ mask) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    long long rx = voxel_of(xyz[3 * i], voxel) - ox, ry = voxel_of(xyz[3 * i + 1], voxel) - oy,
-              rz = voxel_of(xyz[3 * i + 2], voxel) - oz;
-    uint8_t keep = 0;
-    if (rx >= 0 && ry >= 0 && rz >= 0 && rx < kAxisLim && ry < kAxisLim && rz < kAxisLim) {
-        uint64_t key = pack_rel(rx, ry, rz);
-        uint64_t s = mix64(key) & slot_mask;
-        for (;;) {
-            unsigned long long cur = __ldg(set + s);
-            if (cur == key) {
-                keep = 1;
-                break;
-            }
-            if (cur == 0ull) break;
-            s = (s + 1) & slot_mask;
-        }
-    }
-    mask[i] = keep;
+    mask[i] = vox_member_one(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], voxel, ox, oy, oz, set, slot_mask);
+}
+
+// 4 points (3 x 128-bit loads) per thread, uchar4 store
+__global__ void __launch_bounds__(256) k_vox_member4(const float4* __restrict__ xyz4, int64_t n4, float voxel,
+                                                     long long ox, long long oy, long long oz,
+                                                     const unsigned long long* __restrict__ set, uint64_t slot_mask,
+                                                     uchar4* __restrict__ mask4) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n4) return;
+    float4 a = ld_stream_f4(xyz4 + 3 * t), b = ld_stream_f4(xyz4 + 3 * t + 1), c = ld_stream_f4(xyz4 + 3 * t + 2);
+    uchar4 o;
+    o.x = vox_member_one(a.x, a.y, a.z, voxel, ox, oy, oz, set, slot_mask);
+    o.y = vox_member_one(a.w, b.x, b.y, voxel, ox, oy, oz, set, slot_mask);
+    o.z = vox_member_one(b.z, b.w, c.x, voxel, ox, oy, oz, set, slot_mask);
+    o.w = vox_member_one(c.y, c.z, c.w, voxel, ox, oy, oz, set, slot_mask);
+    mask4[t] = o;
 }
 
 int density_member_mask(const float* xyz, int64_t n, float voxel, const int64_t* keep, int64_t n_keep, uint8_t* mask,
@@ -379,9 +456,21 @@ int density_member_mask(const float* xyz, int64_t n, float voxel, const int64_t*
     }
     GSX_CUDA_CHECK(cudaMemcpyAsync(ws, tab.data(), slots * 8, cudaMemcpyHostToDevice, st));
     GSX_CUDA_CHECK(cudaStreamSynchronize(st));  // tab is a stack-owned pageable buffer
-    k_vox_member<<<(int)((n + 255) / 256), 256, 0, st>>>(xyz, n, voxel, o[0], o[1], o[2],
-                                                         (const unsigned long long*)ws, slots - 1, mask);
-    GSX_KERNEL_CHECK();
+    int64_t n4 = 0;
+    if (((uintptr_t)xyz % 16 == 0) && ((uintptr_t)mask % 4 == 0)) {
+        n4 = n / 4;
+        if (n4 > 0) {
+            k_vox_member4<<<(int)((n4 + 255) / 256), 256, 0, st>>>((const float4*)xyz, n4, voxel, o[0], o[1], o[2],
+                                                                    (const unsigned long long*)ws, slots - 1,
+                                                                    (uchar4*)mask);
+            GSX_KERNEL_CHECK();
+        }
+    }
+    if (n - 4 * n4 > 0) {
+        k_vox_member<<<(int)((n - 4 * n4 + 255) / 256), 256, 0, st>>>(xyz, 4 * n4, n, voxel, o[0], o[1], o[2],
+                                                                      (const unsigned long long*)ws, slots - 1, mask);
+        GSX_KERNEL_CHECK();
+    }
     return GSX_OK;
 }
 

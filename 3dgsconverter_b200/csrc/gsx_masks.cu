@@ -54,16 +54,35 @@ int bbox_mask(const float* xyz, int64_t n, const float* lohi, uint8_t* mask, cud
     return GSX_OK;
 }
 
-__global__ void __launch_bounds__(256) k_alpha_mask(const float* __restrict__ op, int64_t n, double t,
+__global__ void __launch_bounds__(256) k_alpha_mask(const float* __restrict__ op, int64_t begin, int64_t n, double t,
                                                     uint8_t* __restrict__ mask) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) mask[i] = (double)op[i] >= t;
+}
+
+__global__ void __launch_bounds__(256) k_alpha_mask4(const float4* __restrict__ op4, int64_t n4, double t,
+                                                     uchar4* __restrict__ mask4) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 v = ld_stream_f4(op4 + i);
+    mask4[i] = make_uchar4((double)v.x >= t, (double)v.y >= t, (double)v.z >= t, (double)v.w >= t);
 }
 
 int alpha_mask(const float* opacity, int64_t n, double logit_thresh, uint8_t* mask, cudaStream_t st) {
     if (n == 0) return GSX_OK;
-    k_alpha_mask<<<(int)((n + 255) / 256), 256, 0, st>>>(opacity, n, logit_thresh, mask);
-    GSX_KERNEL_CHECK();
+    int64_t n4 = 0;
+    if (((uintptr_t)opacity % 16 == 0) && ((uintptr_t)mask % 4 == 0)) {
+        n4 = n / 4;
+        if (n4 > 0) {
+            k_alpha_mask4<<<(int)((n4 + 255) / 256), 256, 0, st>>>((const float4*)opacity, n4, logit_thresh,
+                                                                    (uchar4*)mask);
+            GSX_KERNEL_CHECK();
+        }
+    }
+    if (n - 4 * n4 > 0) {
+        k_alpha_mask<<<(int)((n - 4 * n4 + 255) / 256), 256, 0, st>>>(opacity, 4 * n4, n, logit_thresh, mask);
+        GSX_KERNEL_CHECK();
+    }
     return GSX_OK;
 }
 

@@ -1,6 +1,6 @@
 // gsx_radix.cu -- stable LSD radix sort of (uint64 key, int32 value) pairs, hand-written for sm_100a.
 //
-// Serves the hash-grid build (gpu_ops.py:227 `np.argsort(hashed)`; key = bucket hash << 18 | Morton code)
+// Serves the hash-grid build (gpu_ops.py:227 `np.argsort(hashed)`; key = bucket hash << 15 | Morton code)
 // and the Morton ordering of the exact-KNN path.  8-bit digits; per pass:
 //   k_rs_hist    per-tile digit histogram (tile = 4096 keys, one CTA)  -> hist[digit][tile]
 //   exclusive scan of the digit-major matrix (multi-level block scan)   -> global base of (digit, tile)

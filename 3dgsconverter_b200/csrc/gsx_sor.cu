@@ -5,8 +5,8 @@
 // arithmetic: SURVEY.md Appendix A.1.
 //
 // Design (B200-first, not a translation of the Taichi kernel):
-//   * grid build entirely on device: min/max reduce -> 64-bit key (bucket hash << 18 |
-//     6+6+6-bit Morton code of the position inside the cell) -> radix sort -> float4
+//   * grid build entirely on device: min/max reduce -> 64-bit key (bucket hash << 15 |
+//     5+5+5-bit Morton code of the position inside the cell) -> radix sort -> float4
 //     gather (w carries the original index, so the "unsort" is fused into the query
 //     kernel) -> {start,end} bucket table -> bounding boxes of every aligned run of 32
 //     ("chunk") and 1024 ("super") sorted points.
@@ -40,7 +40,12 @@ namespace gsx {
 #define GSX_D2LIM_BITS 0x60ad78ebu
 #define GSX_FULL 0xffffffffu
 
-constexpr int kMortonBits = 18;
+#ifndef GSX_MORTON_BITS
+#define GSX_MORTON_BITS 15
+#endif
+constexpr int kMortonBits = GSX_MORTON_BITS;       // in-cell Morton code: kMortonBits/3 bits per axis
+constexpr float kMortonScale = (float)(1 << (GSX_MORTON_BITS / 3));
+constexpr float kMortonMax = kMortonScale - 1.f;
 constexpr int kSmallBucket = 64;  // buckets up to this size are scanned without box tests
 constexpr int kQueryBatch = 16;   // consecutive queries grabbed per warp
 
@@ -117,12 +122,17 @@ __global__ void __launch_bounds__(256) k_minmax_partial(const float* __restrict_
 }
 
 __global__ void k_minmax_final(const float* __restrict__ partial, int nblocks, float* __restrict__ out) {
-    int a = threadIdx.x;
-    if (a < 6) {
-        float r = partial[a];
-        for (int b = 1; b < nblocks; ++b) r = a < 3 ? fminf(r, partial[b * 6 + a]) : fmaxf(r, partial[b * 6 + a]);
-        out[a] = r;
+    // 6 warps, warp a reduces component a over the block partials
+    const int a = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (a >= 6) return;
+    float r = a < 3 ? INFINITY : -INFINITY;
+    for (int b = lane; b < nblocks; b += 32) r = a < 3 ? fminf(r, partial[b * 6 + a]) : fmaxf(r, partial[b * 6 + a]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float t = __shfl_xor_sync(GSX_FULL, r, o);
+        r = a < 3 ? fminf(r, t) : fmaxf(r, t);
     }
+    if (lane == 0) out[a] = r;
 }
 
 int sor_minmax(const float* xyz, int64_t n, float* minmax_dev, float* partial, cudaStream_t st) {
@@ -133,7 +143,7 @@ int sor_minmax(const float* xyz, int64_t n, float* minmax_dev, float* partial, c
     if (blocks < 1) blocks = 1;
     k_minmax_partial<<<blocks, 256, 0, st>>>(xyz, n, partial);
     GSX_KERNEL_CHECK();
-    k_minmax_final<<<1, 32, 0, st>>>(partial, blocks, minmax_dev);
+    k_minmax_final<<<1, 192, 0, st>>>(partial, blocks, minmax_dev);
     GSX_KERNEL_CHECK();
     return GSX_OK;
 }
@@ -171,9 +181,9 @@ __global__ void __launch_bounds__(256) k_sor_keys(const float* __restrict__ xyz,
         if (h < 0) h += n;
     }
     // position inside the cell, 6 bits per axis (ordering only -- never affects results)
-    uint32_t sx = (uint32_t)fminf(63.f, fmaxf(0.f, (fx - flx) * 64.f));
-    uint32_t sy = (uint32_t)fminf(63.f, fmaxf(0.f, (fy - fly) * 64.f));
-    uint32_t sz = (uint32_t)fminf(63.f, fmaxf(0.f, (fz - flz) * 64.f));
+    uint32_t sx = (uint32_t)fminf(kMortonMax, fmaxf(0.f, (fx - flx) * kMortonScale));
+    uint32_t sy = (uint32_t)fminf(kMortonMax, fmaxf(0.f, (fy - fly) * kMortonScale));
+    uint32_t sz = (uint32_t)fminf(kMortonMax, fmaxf(0.f, (fz - flz) * kMortonScale));
     uint32_t mort = (spread6(sx) << 2) | (spread6(sy) << 1) | spread6(sz);
     keys[i] = ((uint64_t)h << kMortonBits) | (uint64_t)mort;
     vals[i] = (int32_t)i;
@@ -356,9 +366,9 @@ __device__ __forceinline__ uint64_t bucket_key(float x, float y, float z, float 
         h = hx % n;
         if (h < 0) h += n;
     }
-    uint32_t sx = (uint32_t)fminf(63.f, fmaxf(0.f, (fx - flx) * 64.f));
-    uint32_t sy = (uint32_t)fminf(63.f, fmaxf(0.f, (fy - fly) * 64.f));
-    uint32_t sz = (uint32_t)fminf(63.f, fmaxf(0.f, (fz - flz) * 64.f));
+    uint32_t sx = (uint32_t)fminf(kMortonMax, fmaxf(0.f, (fx - flx) * kMortonScale));
+    uint32_t sy = (uint32_t)fminf(kMortonMax, fmaxf(0.f, (fy - fly) * kMortonScale));
+    uint32_t sz = (uint32_t)fminf(kMortonMax, fmaxf(0.f, (fz - flz) * kMortonScale));
     uint32_t mort = (spread6(sx) << 2) | (spread6(sy) << 1) | spread6(sz);
     return ((uint64_t)h << kMortonBits) | (uint64_t)mort;
 }

@@ -94,7 +94,7 @@ int gsx_sor_mean_dists_range(int64_t n, int64_t q_begin, int64_t q_end, int32_t 
 
 /* gpu_ops.py:227 (np.argsort of the bucket hashes): stable LSD radix sort, in place, of (uint64 key, int32
  * value) pairs on the key bits [begin_bit, end_bit).  The hash-grid build uses it with key =
- * hash << 18 | Morton code and value = original index. */
+ * hash << 15 | Morton code and value = original index. */
 int64_t gsx_sort_pairs_workspace_bytes(int64_t n);
 int gsx_sort_pairs(uint64_t* keys_dev, int32_t* vals_dev, int64_t n, int32_t begin_bit, int32_t end_bit, void* ws,
                    int64_t ws_bytes, void* stream);
