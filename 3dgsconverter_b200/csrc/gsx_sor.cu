@@ -46,8 +46,14 @@ namespace gsx {
 constexpr int kMortonBits = GSX_MORTON_BITS;       // in-cell Morton code: kMortonBits/3 bits per axis
 constexpr float kMortonScale = (float)(1 << (GSX_MORTON_BITS / 3));
 constexpr float kMortonMax = kMortonScale - 1.f;
-constexpr int kSmallBucket = 64;  // buckets up to this size are scanned without box tests
-constexpr int kQueryBatch = 16;   // consecutive queries grabbed per warp
+#ifndef GSX_SMALL_BUCKET
+#define GSX_SMALL_BUCKET 64
+#endif
+constexpr int kSmallBucket = GSX_SMALL_BUCKET;  // buckets up to this size are scanned without box tests
+#ifndef GSX_QUERY_BATCH
+#define GSX_QUERY_BATCH 16
+#endif
+constexpr int kQueryBatch = GSX_QUERY_BATCH;   // consecutive queries grabbed per warp
 
 // ------------------------------------------------------------------ workspace layout
 
@@ -670,7 +676,7 @@ __device__ __forceinline__ void scan32(const float4* __restrict__ spos, int64_t 
 }
 
 #ifndef GSX_KNN_MINBLOCKS
-#define GSX_KNN_MINBLOCKS 6
+#define GSX_KNN_MINBLOCKS 8
 #endif
 template <int NREG, bool STATS>
 __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
