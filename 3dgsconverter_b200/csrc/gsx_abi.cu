@@ -11,6 +11,7 @@
 #include "gsx_knn_exact.cuh"
 #include "gsx_masks.cuh"
 #include "gsx_radix.cuh"
+#include "gsx_sog.cuh"
 #include "gsx_sor.cuh"
 
 #include <atomic>
@@ -377,6 +378,19 @@ int gsx_density_grid_dense(const int32_t* grid_dev, const int64_t* q0, const int
                            int64_t* n_voxels_host, void* ws, int64_t ws_bytes, void* stream) {
     return density_grid_dense(grid_dev, q0, dim, min_points, dense_vox_host, dense_cnt_host, cap, n_dense_host,
                               n_voxels_host, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+/* ------------------------------------------------------------------ SOG writer helpers */
+
+int64_t gsx_lexsort_workspace_bytes(int64_t n) { return lexsort_workspace_bytes(n); }
+
+int gsx_lexsort_zyx(const float* xyz_dev, int64_t n, int32_t* order_dev, void* ws, int64_t ws_bytes, void* stream) {
+    return lexsort_zyx(xyz_dev, n, order_dev, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+int gsx_quantize_to_codebook(const float* vals_dev, int64_t n, const float* codebook_host, int32_t m,
+                             uint8_t* labels_dev, void* ws, int64_t ws_bytes, void* stream) {
+    return quantize_to_codebook(vals_dev, n, codebook_host, m, labels_dev, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 /* ------------------------------------------------------------------ K-Means */

@@ -67,6 +67,9 @@ _SIGS = {
     "gsx_density_grid_count": (C.c_int, [_vp, _i64, C.c_float, C.POINTER(_i64), C.POINTER(_i64), _vp, _vp, _vp]),
     "gsx_density_grid_dense": (C.c_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), _i64, _vp, _vp, _i64,
                                          C.POINTER(_i64), C.POINTER(_i64), _vp, _i64, _vp]),
+    "gsx_lexsort_workspace_bytes": (_i64, [_i64]),
+    "gsx_lexsort_zyx": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp]),
+    "gsx_quantize_to_codebook": (C.c_int, [_vp, _i64, _f32p, _i32, _vp, _vp, _i64, _vp]),
     "gsx_kmeans_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32]),
     "gsx_kmeans_lloyd_device": (C.c_int, [_vp, C.POINTER(_i64), _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64,
                                           _vp]),

@@ -173,6 +173,16 @@ int gsx_density_grid_dense(const int32_t* grid_dev, const int64_t* q0, const int
                            int64_t* dense_vox_host, int32_t* dense_cnt_host, int64_t cap, int64_t* n_dense_host,
                            int64_t* n_voxels_host, void* ws, int64_t ws_bytes, void* stream);
 
+/* ---- SOG writer helpers, the steps either side of K-Means ------------------- */
+/* formats/sog.py:264  np.lexsort((z, y, x)): order_dev[j] = index of the j-th splat in (x, then y, then z) order,
+ * stable; -0.0 == +0.0 as in NumPy.  (NaN coordinates are not supported.) */
+int64_t gsx_lexsort_workspace_bytes(int64_t n);
+int gsx_lexsort_zyx(const float* xyz_dev, int64_t n, int32_t* order_dev, void* ws, int64_t ws_bytes, void* stream);
+/* formats/sog.py:408-419 quantize_to_codebook: index of the nearest entry of an ascending float32 codebook
+ * (searchsorted-left, clip, prefer the left neighbour if strictly closer), as uint8.  1 <= m <= 4096; ws >= 4*m B. */
+int gsx_quantize_to_codebook(const float* vals_dev, int64_t n, const float* codebook_host, int32_t m,
+                             uint8_t* labels_dev, void* ws, int64_t ws_bytes, void* stream);
+
 /* ---- K-Means: gpu_ops.py:57-96 (kernels) + :186-188 (Lloyd loop) ---------------------- */
 /* Batched over `nprob` independent problems stored back to back (SOG shN chunks, sog.py:527-549):
  * problem p has rows [row_off[p], row_off[p+1]) of X[*,D] and K centroids at C[p*K*D].
