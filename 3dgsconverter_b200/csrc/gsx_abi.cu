@@ -399,6 +399,9 @@ int64_t gsx_kmeans_workspace_bytes(int64_t n_total, int32_t nprob, int32_t K, in
     return kmeans_workspace_bytes(n_total, nprob, K, D);
 }
 
+void gsx_kmeans_set_prefilter(int32_t on) { kmeans_set_prefilter(on); }
+int32_t gsx_kmeans_get_prefilter(void) { return kmeans_get_prefilter(); }
+
 int gsx_kmeans_lloyd_device(const float* X_dev, const int64_t* row_off_host, int32_t nprob, int32_t K, int32_t D,
                             int32_t max_iter, float* C_dev, int32_t* labels_dev, int32_t* counts_dev, void* ws,
                             int64_t ws_bytes, void* stream) {

@@ -132,6 +132,207 @@ __global__ void __launch_bounds__(kAssignThreads)
         if (live[p]) labels[row[p]] = best_k[p];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Exact pre-filter (optional, gsx_kmeans_set_prefilter): the contract's distance costs 3 FP32 instructions
+// per (point, centroid, dim).  Here every centroid is first scored with ONE fma per dim,
+//     s_c = x.c - 0.5*||c||^2        (so that  E_c = ||x||^2 - 2 s_c  is the squared distance),
+// and only the centroids whose score is within a rigorous rounding-error margin of the best score are then
+// evaluated with the strict (sub, mul, add -- no fma, dims ascending) distance of SURVEY A.5, lowest index
+// winning ties.  Let c* be the contract's answer, c' the best-scoring centroid, delta >= |(-2 s_c) - (||c||^2 -
+// 2 x.c)| the fma-chain error bound gamma_{2D} (Cmax^2 + 2 ||x|| Cmax), and g' = 2 gamma_{D+2}/(1-gamma_{D+2})
+// the bound of the strict evaluation.  Then  s_{c*} >= s_{c'} - (delta + g'/2 * E_{c'})  (DESIGN.md §4.6), so a
+// candidate set with margin 2*delta + g' * (||x||^2 - 2 s_max + delta) (twice the bound) always contains c*.
+// Up to kPreCand candidates per point live in shared memory; overflow (many near-ties) or a non-finite margin
+// falls back to the full strict scan, so the labels are bit-identical to k_kmeans_assign in every case.
+constexpr int kPreCand = 8;
+
+template <int D>
+__device__ __forceinline__ float strict_dist(const float* __restrict__ x, const float* __restrict__ c) {
+    float acc = 0.f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        float df = __fsub_rn(x[d], __ldg(c + d));
+        acc = __fadd_rn(acc, __fmul_rn(df, df));
+    }
+    return acc;
+}
+
+// per problem: an upper bound of max_c ||c|| (input of the error margin)
+__global__ void __launch_bounds__(256) k_kmeans_cmax(const float* __restrict__ C, int K, int D,
+                                                     float* __restrict__ cmax) {
+    const float* Cp = C + (size_t)blockIdx.x * K * D;
+    float m = 0.f;
+    for (int c = threadIdx.x; c < K; c += blockDim.x) {
+        float cn = 0.f;
+        for (int d = 0; d < D; ++d) {
+            float v = Cp[(size_t)c * D + d];
+            cn = __fmaf_rn(v, v, cn);
+        }
+        m = fmaxf(m, cn);
+    }
+    __shared__ float sm[256];
+    sm[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sm[threadIdx.x] = fmaxf(sm[threadIdx.x], sm[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) cmax[blockIdx.x] = sqrtf(sm[0]) * 1.0001f;
+}
+
+template <int D, int P>
+__global__ void __launch_bounds__(kAssignThreads)
+    k_kmeans_assign_pre(const float* __restrict__ X, const float* __restrict__ C, int* __restrict__ labels,
+                        const KmProb* __restrict__ probs, int nprob, int K, const float* __restrict__ cmax) {
+    constexpr int DP = (D + 3) / 4 * 4;
+    constexpr int G = DP / 4;
+    __shared__ __align__(16) float sc[kCentTile * DP];
+    __shared__ float shalf[kCentTile];                              // -0.5 * ||c||^2
+    __shared__ float cand_s[kPreCand][P][kAssignThreads];           // [slot][point][thread]: conflict-free
+    __shared__ int cand_i[kPreCand][P][kAssignThreads];
+
+    int lo = 0, hi = nprob - 1;
+    while (lo < hi) {
+        int mid = (lo + hi + 1) >> 1;
+        if (probs[mid].tile0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    const KmProb pr = probs[lo];
+    const long long tile = (long long)blockIdx.x - pr.tile0;
+    const float* Cp = C + (size_t)lo * K * D;
+    const int tid = threadIdx.x;
+
+    float x[P][DP];
+    long long row[P];
+    bool live[P];
+    float smax[P], marg[P], xnu[P], delta[P];
+    int ncand[P];
+    bool ovf[P];
+    const float Cm = cmax[lo];
+    constexpr float kU = 5.9604645e-8f;                              // 2^-24
+    constexpr float kGam2D = (2 * D + 2) * kU * 1.02f;               // >= gamma_{2D}
+    constexpr float kGs = 2.f * (D + 3) * kU * 1.02f;                // >= 2 gamma_{D+2} / (1 - gamma_{D+2})
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        long long r = tile * (kAssignThreads * P) + p * kAssignThreads + tid;
+        live[p] = r < pr.rows;
+        row[p] = pr.row0 + (live[p] ? r : 0);
+        const float* xr = X + (size_t)row[p] * D;
+        float xn = 0.f;
+#pragma unroll
+        for (int d = 0; d < DP; ++d) {
+            x[p][d] = d < D ? xr[d] : 0.f;
+            xn = __fmaf_rn(x[p][d], x[p][d], xn);
+        }
+        xnu[p] = xn * 1.0001f;                                       // >= ||x||^2
+        const float xnorm = sqrtf(xnu[p]) * 1.0001f;
+        delta[p] = kGam2D * (Cm * Cm + 2.f * xnorm * Cm) * 1.01f + 1e-37f;
+        smax[p] = -3.0e38f;
+        marg[p] = INFINITY;
+        ncand[p] = 0;
+        ovf[p] = false;
+    }
+    auto margin_of = [&](int p) {  // twice the proven bound, in the score domain
+        float e_ub = fmaxf(xnu[p] - 2.f * smax[p] + delta[p], 0.f);
+        return 2.f * delta[p] + kGs * e_ub + 1e-37f;
+    };
+    auto consider = [&](int p, int c, float sv) {
+        if (!(sv >= smax[p] - marg[p])) return;
+        if (sv > smax[p]) {
+            smax[p] = sv;
+            marg[p] = margin_of(p);
+        }
+        int nc = ncand[p];
+        if (nc == kPreCand) {  // drop the entries that fell out of the margin of the current best
+            const float thr = smax[p] - marg[p];
+            int w = 0;
+            for (int r = 0; r < kPreCand; ++r) {
+                float cs = cand_s[r][p][tid];
+                if (cs >= thr) {
+                    cand_s[w][p][tid] = cs;
+                    cand_i[w][p][tid] = cand_i[r][p][tid];
+                    ++w;
+                }
+            }
+            nc = w;
+        }
+        if (nc < kPreCand) {
+            cand_s[nc][p][tid] = sv;
+            cand_i[nc][p][tid] = c;
+            ncand[p] = nc + 1;
+        } else {
+            ncand[p] = nc;
+            ovf[p] = true;
+        }
+    };
+
+    for (int k0 = 0; k0 < K; k0 += kCentTile) {
+        const int kt = K - k0 < kCentTile ? K - k0 : kCentTile;
+        __syncthreads();
+        for (int t = tid; t < kCentTile * DP; t += kAssignThreads) {
+            int c = t / DP, d = t - c * DP;
+            sc[t] = (c < kt && d < D) ? Cp[(size_t)(k0 + c) * D + d] : 0.f;
+        }
+        __syncthreads();
+        if (tid < kCentTile) {
+            float cn = 0.f;
+            for (int d = 0; d < D; ++d) cn = __fmaf_rn(sc[tid * DP + d], sc[tid * DP + d], cn);
+            shalf[tid] = -0.5f * cn;
+        }
+        __syncthreads();
+        for (int c = 0; c < kt; c += 4) {  // kCentTile is a multiple of 4; rows >= kt are zero and ignored
+            float acc[4][P];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int p = 0; p < P; ++p) acc[q][p] = shalf[c + q];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                float4 r4[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) r4[q] = reinterpret_cast<const float4*>(sc + (c + q) * DP)[g];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float cv[4] = {r4[q].x, r4[q].y, r4[q].z, r4[q].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        if (g * 4 + e < D) {
+#pragma unroll
+                            for (int p = 0; p < P; ++p) acc[q][p] = __fmaf_rn(x[p][g * 4 + e], cv[e], acc[q][p]);
+                        }
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (c + q < kt) {
+#pragma unroll
+                    for (int p = 0; p < P; ++p) consider(p, k0 + c + q, acc[q][p]);
+                }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p) {
+        if (!live[p]) continue;
+        float best = 1e20f;
+        int bk = -1;
+        const bool exact_all = ovf[p] || !(marg[p] < 3.0e38f) || !(smax[p] > -3.0e38f);
+        if (exact_all) {
+            for (int c = 0; c < K; ++c) {
+                float dist = strict_dist<D>(x[p], Cp + (size_t)c * D);
+                if (dist < best) best = dist, bk = c;
+            }
+        } else {
+            const float thr = smax[p] - marg[p];
+            for (int r = 0; r < ncand[p]; ++r) {  // ascending centroid index: strict '<' keeps the lowest on ties
+                if (!(cand_s[r][p][tid] >= thr)) continue;
+                const int c = cand_i[r][p][tid];
+                float dist = strict_dist<D>(x[p], Cp + (size_t)c * D);
+                if (dist < best) best = dist, bk = c;
+            }
+        }
+        labels[row[p]] = bk;
+    }
+}
+
 // any D: one point per thread, x re-read through L1 (slow path for unusual dimensions)
 __global__ void __launch_bounds__(kAssignThreads)
     k_kmeans_assign_generic(const float* __restrict__ X, const float* __restrict__ C, int* __restrict__ labels,
@@ -397,6 +598,7 @@ struct KmWs {
     int* hist;
     int* totals;
     int* offs;
+    float* cmax;
     size_t total;
     bool ok;
 };
@@ -410,6 +612,7 @@ static KmWs km_carve(void* ws, size_t bytes, int64_t n_total, int nprob, int K, 
     w.hist = c.take<int>(sorted ? (size_t)nsub * (K + 1) : 1);
     w.totals = c.take<int>(sorted ? (size_t)nprob * (K + 1) : 1);
     w.offs = c.take<int>(sorted ? (size_t)nprob * (K + 1) : 1);
+    w.cmax = c.take<float>((size_t)nprob + 8);
     w.total = align_up(c.off, 256);
     w.ok = c.ok();
     return w;
@@ -425,10 +628,22 @@ int64_t kmeans_workspace_bytes(int64_t n_total, int nprob, int K, int D) {
     return (int64_t)w.total + 1024;
 }
 
+static int g_prefilter = 0;
+void kmeans_set_prefilter(int on) { g_prefilter = on ? 1 : 0; }
+int kmeans_get_prefilter() { return g_prefilter; }
+
 template <int D>
 static void launch_assign(const float* X, const float* C, int* labels, const KmProb* probs, int nprob, int K,
-                          int tiles, cudaStream_t st) {
+                          int tiles, const float* cmax, cudaStream_t st) {
     constexpr int P = PointsPerThread<D>::value;
+    if constexpr (D >= 9) {
+        if (g_prefilter && cmax) {
+            k_kmeans_cmax<<<nprob, 256, 0, st>>>(C, K, D, const_cast<float*>(cmax));
+            count_launch();
+            k_kmeans_assign_pre<D, P><<<tiles, kAssignThreads, 0, st>>>(X, C, labels, probs, nprob, K, cmax);
+            return;
+        }
+    }
     k_kmeans_assign<D, P><<<tiles, kAssignThreads, 0, st>>>(X, C, labels, probs, nprob, K);
 }
 
@@ -482,13 +697,13 @@ int kmeans_lloyd(const float* X, const int64_t* row_off, int nprob, int K, int D
     }
     for (int it = 0; it < max_iter; ++it) {
         switch (D) {
-            case 1: launch_assign<1>(X, C, labels, dp, nprob, K, (int)tiles, st); break;
-            case 2: launch_assign<2>(X, C, labels, dp, nprob, K, (int)tiles, st); break;
-            case 3: launch_assign<3>(X, C, labels, dp, nprob, K, (int)tiles, st); break;
-            case 4: launch_assign<4>(X, C, labels, dp, nprob, K, (int)tiles, st); break;
-            case 9: launch_assign<9>(X, C, labels, dp, nprob, K, (int)tiles, st); break;
-            case 24: launch_assign<24>(X, C, labels, dp, nprob, K, (int)tiles, st); break;
-            case 45: launch_assign<45>(X, C, labels, dp, nprob, K, (int)tiles, st); break;
+            case 1: launch_assign<1>(X, C, labels, dp, nprob, K, (int)tiles, w.cmax, st); break;
+            case 2: launch_assign<2>(X, C, labels, dp, nprob, K, (int)tiles, w.cmax, st); break;
+            case 3: launch_assign<3>(X, C, labels, dp, nprob, K, (int)tiles, w.cmax, st); break;
+            case 4: launch_assign<4>(X, C, labels, dp, nprob, K, (int)tiles, w.cmax, st); break;
+            case 9: launch_assign<9>(X, C, labels, dp, nprob, K, (int)tiles, w.cmax, st); break;
+            case 24: launch_assign<24>(X, C, labels, dp, nprob, K, (int)tiles, w.cmax, st); break;
+            case 45: launch_assign<45>(X, C, labels, dp, nprob, K, (int)tiles, w.cmax, st); break;
             default:
                 k_kmeans_assign_generic<<<(int)tiles, kAssignThreads, 0, st>>>(X, C, labels, dp, nprob, K, D);
         }

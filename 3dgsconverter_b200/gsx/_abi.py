@@ -71,6 +71,8 @@ _SIGS = {
     "gsx_lexsort_zyx": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp]),
     "gsx_quantize_to_codebook": (C.c_int, [_vp, _i64, _f32p, _i32, _vp, _vp, _i64, _vp]),
     "gsx_kmeans_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32]),
+    "gsx_kmeans_set_prefilter": (None, [_i32]),
+    "gsx_kmeans_get_prefilter": (_i32, []),
     "gsx_kmeans_lloyd_device": (C.c_int, [_vp, C.POINTER(_i64), _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64,
                                           _vp]),
     "gsx_kmeans_host": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp]),

@@ -6,8 +6,23 @@ import ctypes as C
 import numpy as np
 import torch
 
+import os
+
 from ._abi import lib, check
 from .sor import _ptr, _stream
+
+
+def set_prefilter(on: bool):
+    """Exact fma pre-filter of the assign step (labels bit-identical either way); see csrc/gsx_kmeans.cu."""
+    lib.gsx_kmeans_set_prefilter(1 if on else 0)
+
+
+def prefilter_enabled() -> bool:
+    return bool(lib.gsx_kmeans_get_prefilter())
+
+
+if "GSX_KMEANS_PREFILTER" in os.environ:
+    set_prefilter(os.environ["GSX_KMEANS_PREFILTER"] == "1")
 
 
 def kmeans_lloyd_batched(X: torch.Tensor, row_off, K: int, max_iter: int, init: torch.Tensor):

@@ -189,6 +189,11 @@ int gsx_quantize_to_codebook(const float* vals_dev, int64_t n, const float* code
  * One call = max_iter x (assign ; update) with the serial index-order float32 sums of SURVEY A.5.
  * labels are those of the last assign (one update behind C); counts int32[nprob*K]. */
 int64_t gsx_kmeans_workspace_bytes(int64_t n_total, int32_t nprob, int32_t K, int32_t D);
+/* Exact pre-filter of the assign step (D >= 9): one fma per (point, centroid, dim) scores every centroid, the strict
+ * contract distance is evaluated only for the centroids within a proven rounding-error margin of the best score.
+ * Labels are bit-identical either way; process-wide switch, default off. */
+void gsx_kmeans_set_prefilter(int32_t on);
+int32_t gsx_kmeans_get_prefilter(void);
 int gsx_kmeans_lloyd_device(const float* X_dev, const int64_t* row_off_host, int32_t nprob, int32_t K, int32_t D,
                             int32_t max_iter, float* C_dev, int32_t* labels_dev, int32_t* counts_dev, void* ws,
                             int64_t ws_bytes, void* stream);

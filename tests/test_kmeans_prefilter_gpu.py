@@ -1,0 +1,51 @@
+"""GPU: K-Means with the exact fma pre-filter switched on is bit-identical to the oracle (labels, counts,
+centroids), including adversarial near-tie inputs and the overflow fallback."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def prefilter_on(gsx_lib):
+    from gsx import kmeans as gk
+    old = gk.prefilter_enabled()
+    gk.set_prefilter(True)
+    yield
+    gk.set_prefilter(old)
+
+
+def _check(X, k, it, cuda, seed=1234):
+    import torch
+    import oracle
+    from gsx import kmeans as gk
+    np.random.seed(seed)
+    init = oracle.kmeans_reference_init(X, k)
+    Co, Lo, cnto = oracle.kmeans_lloyd(X, k, it, init=init)
+    C, L, cnt = gk.kmeans_lloyd(torch.from_numpy(X).to(cuda), k, it, torch.from_numpy(init).to(cuda))
+    assert np.array_equal(L.cpu().numpy(), Lo)
+    assert np.array_equal(cnt.cpu().numpy(), cnto)
+    assert np.array_equal(C.cpu().numpy().view(np.uint32), Co.view(np.uint32))
+
+
+@pytest.mark.parametrize("n,d,k,it", [(100_000, 45, 256, 3), (20_000, 45, 64, 5), (10_000, 24, 100, 3),
+                                      (10_000, 9, 16, 10), (4_000, 45, 300, 2)])
+def test_prefilter_matches_oracle(n, d, k, it, cuda, prefilter_on):
+    from gsx import synth
+    X = np.ascontiguousarray(synth.attributes(n)["f_rest"][:, :d])
+    _check(X, k, it, cuda)
+
+
+def test_prefilter_adversarial(cuda, prefilter_on):
+    rng = np.random.default_rng(0)
+    base = rng.normal(0, 0.15, (3000, 45)).astype(np.float32)
+    # many exactly duplicated rows -> the init draws duplicate centroids: > 8 exact ties -> overflow fallback
+    X = np.ascontiguousarray(np.repeat(base[:150], 20, axis=0))
+    _check(X, 64, 3, cuda, seed=3)
+    # large common offset: heavy cancellation in ||x||^2 - 2 x.c + ||c||^2
+    _check(np.ascontiguousarray(base + np.float32(100.0)), 50, 3, cuda)
+    # lattice: exact distance ties between different centroids (lowest index must win)
+    Xg = rng.integers(-2, 3, (5000, 9)).astype(np.float32)
+    _check(Xg, 40, 4, cuda)
+    # distances around the 1e20 start value (label -1 rows are skipped by the update)
+    _check(np.ascontiguousarray(base * np.float32(3e10)), 32, 2, cuda)
