@@ -320,8 +320,8 @@ def main():
         line["e2e"] = measure_e2e(xyz_np, args)
         line["cpu_baseline"] = measure_cpu_baseline(xyz_np, args)
         line["other_modes"] = measure_other(xyz, ws, means, args)
-        line["kmeans"] = measure_kmeans(dev)
         line["pipeline"] = measure_pipeline(xyz_np, args)
+        line["kmeans"] = measure_kmeans(dev)
     elif world > 1:
         line["e2e"] = measure_e2e_sharded(xyz_np, args, dev, rank, world)
     if rank == 0:
@@ -493,11 +493,27 @@ def measure_kmeans(dev):
     ms = a.elapsed_time(b)
     chunk_iters = nprob * iters
     flops = 3.0 * nprob * rows * K * D * iters
-    return {"metric": "K-Means chunk-iterations/s (781250x45, K=256)", "value": round(chunk_iters / (ms * 1e-3), 2),
-            "ms_total": round(ms, 2), "chunks": nprob, "iters": iters,
-            "fp32_lane_instr_per_s_T": round(flops / (ms * 1e-3) / 1e12, 2),
-            "fp32_no_fma_peak_T": 37.2, "frac_of_fp32_peak": round(flops / (ms * 1e-3) / 1e12 / 37.2, 3),
-            "mpoint_iters_per_s": round(nprob * rows * iters / (ms * 1e-3) / 1e6, 1)}
+    out = {"metric": "K-Means chunk-iterations/s (781250x45, K=256)", "value": round(chunk_iters / (ms * 1e-3), 2),
+           "ms_total": round(ms, 2), "chunks": nprob, "iters": iters,
+           "fp32_lane_instr_per_s_T": round(flops / (ms * 1e-3) / 1e12, 2),
+           "fp32_no_fma_peak_T": 37.2, "frac_of_fp32_peak": round(flops / (ms * 1e-3) / 1e12 / 37.2, 3),
+           "mpoint_iters_per_s": round(nprob * rows * iters / (ms * 1e-3) / 1e6, 1)}
+    # the exact fma pre-filter (bit-identical labels, off by default in round 1): timed last, best effort
+    try:
+        gk.set_prefilter(True)
+        gk.kmeans_lloyd_batched(X, offs, K, 1, init)
+        torch.cuda.synchronize()
+        a.record()
+        gk.kmeans_lloyd_batched(X, offs, K, iters, init)
+        b.record()
+        torch.cuda.synchronize()
+        ms2 = a.elapsed_time(b)
+        out["with_exact_prefilter"] = {"value": round(chunk_iters / (ms2 * 1e-3), 2), "ms_total": round(ms2, 2)}
+    except Exception as e:  # noqa: BLE001
+        out["with_exact_prefilter"] = {"error": str(e)[:200]}
+    finally:
+        gk.set_prefilter(False)
+    return out
 
 
 if __name__ == "__main__":
