@@ -513,6 +513,20 @@ def measure_kmeans(dev):
         out["with_exact_prefilter"] = {"error": str(e)[:200]}
     finally:
         gk.set_prefilter(False)
+    # the reference's CPU path for the same call (gpu_ops.py:48-52: scikit-learn MiniBatchKMeans, unseeded --
+    # a different algorithm whose "iterations" are mini-batch passes): one 781 250 x 45 chunk, K=256, max_iter=10
+    try:
+        from sklearn.cluster import MiniBatchKMeans
+        xc = X[:rows].cpu().numpy()
+        t0 = time.perf_counter()
+        MiniBatchKMeans(n_clusters=K, max_iter=10, batch_size=min(4096 * 4, len(xc)), n_init="auto",
+                        compute_labels=True).fit(xc)
+        dt = time.perf_counter() - t0
+        out["cpu_reference_sklearn"] = {"seconds_per_chunk_max_iter10": round(dt, 2),
+                                        "chunk_fits_per_s": round(1.0 / dt, 3), "cores": os.cpu_count(),
+                                        "note": "the reference's fallback when Taichi is absent; one full chunk"}
+    except Exception as e:  # noqa: BLE001
+        out["cpu_reference_sklearn"] = {"error": str(e)[:200]}
     return out
 
 
