@@ -160,14 +160,65 @@ def _owner_bounds(n_global: int, world: int):
     return [(o * n_global + world - 1) // world for o in range(world + 1)]
 
 
-def build_grid_distributed(xyz_local: torch.Tensor, group=None):
-    """Hash grid of the UNION cloud without replicating the sort: local sort of the slab by global bucket key
-    -> all-to-all by bucket owner -> owner-local sort -> all-gather of the sorted float4 segments ->
-    table / boxes filled locally.  Returns (SorGrid over n_global points, sizes of the slabs)."""
-    import ctypes as C
-    from . import sor
-    from ._abi import lib, check
-    from .sor import _ptr, _stream
+class _GsxBuildOps:
+    """Device stages of the distributed grid build (replaceable in CPU/gloo tests)."""
+
+    def cell_size(self, mm: np.ndarray, n_global: int) -> float:
+        import ctypes as C
+        from ._abi import lib
+        return float(lib.gsx_sor_cell_size(mm.ctypes.data_as(C.POINTER(C.c_float)), n_global))
+
+    def local_run(self, xyz_local, idx_base, n_global, world, bmin, cell):
+        """A: stable partition of the slab by bucket owner.  Returns (pos4 [n,4] float32, cuts int64[world+1])."""
+        import ctypes as C
+        from . import sor
+        from ._abi import lib, check
+        from .sor import _ptr, _stream
+        dev = xyz_local.device
+        n_local = xyz_local.shape[0]
+        ws_l = sor.workspace(max(n_local, 1), dev)
+        pos4 = torch.empty((n_local, 4), dtype=torch.float32, device=dev)
+        cuts = torch.zeros(world + 1, dtype=torch.int64, device=dev)
+        check(lib.gsx_sor_dist_local_run(_ptr(xyz_local), n_local, idx_base, n_global, world,
+                                         bmin.ctypes.data_as(C.POINTER(C.c_float)), cell, _ptr(pos4), _ptr(cuts),
+                                         _ptr(ws_l), ws_l.numel(), _stream()), "gsx_sor_dist_local_run")
+        return pos4, cuts
+
+    def merge_into(self, pos4_r, n_global, bmin, cell, out):
+        """B: sort the received points of this rank's bucket range by (bucket, in-cell Morton) into `out`."""
+        import ctypes as C
+        from . import sor
+        from ._abi import lib, check
+        from .sor import _ptr, _stream
+        m = pos4_r.shape[0]
+        ws_m = sor.workspace(max(m, 1), pos4_r.device)
+        check(lib.gsx_sor_dist_merge(_ptr(pos4_r), m, n_global, bmin.ctypes.data_as(C.POINTER(C.c_float)), cell,
+                                     _ptr(out), _ptr(ws_m), ws_m.numel(), _stream()), "gsx_sor_dist_merge")
+
+    def new_grid_storage(self, n_global, dev):
+        """Workspace of the final grid and a [n_global,4] view of its sorted-position array (all-gather target)."""
+        from . import sor
+        from ._abi import lib
+        ws = sor.workspace(n_global, dev)
+        off = lib.gsx_sor_spos_offset(n_global)
+        return ws, ws[off: off + n_global * 16].view(torch.float32).view(n_global, 4)
+
+    def finish(self, ws, spos_full, n_global, bmin, cell):
+        """C: table, boxes and bucket boxes from the globally sorted array."""
+        import ctypes as C
+        from . import sor
+        from ._abi import lib, check
+        from .sor import _ptr, _stream
+        check(lib.gsx_sor_build_from_sorted(_ptr(spos_full), n_global, bmin.ctypes.data_as(C.POINTER(C.c_float)), cell,
+                                            _ptr(ws), ws.numel(), _stream()), "gsx_sor_build_from_sorted")
+        return sor.SorGrid(n_global, ws, bmin, cell)
+
+
+def build_grid_distributed(xyz_local: torch.Tensor, group=None, ops=None):
+    """Hash grid of the UNION cloud without replicating the sort: partition of the slab by bucket owner ->
+    all-to-all -> owner-local sort -> all-gather of the sorted float4 segments -> table / boxes filled locally.
+    Returns (grid over n_global points, sizes of the slabs)."""
+    ops = ops or _GsxBuildOps()
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     dev = xyz_local.device
@@ -184,15 +235,10 @@ def build_grid_distributed(xyz_local: torch.Tensor, group=None):
     dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=group)
     dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=group)
     mm = torch.cat([lo, hi]).cpu().numpy().astype(np.float32)
-    cell = float(lib.gsx_sor_cell_size(mm.ctypes.data_as(C.POINTER(C.c_float)), n_global))
+    cell = ops.cell_size(mm, n_global)
     bmin = mm[:3].copy()
-    bminp = bmin.ctypes.data_as(C.POINTER(C.c_float))
     # A. stable partition of the slab by bucket owner (one radix pass) + float4 gather
-    ws_l = sor.workspace(max(n_local, 1), dev)
-    pos4 = torch.empty((n_local, 4), dtype=torch.float32, device=dev)
-    cuts = torch.zeros(world + 1, dtype=torch.int64, device=dev)
-    check(lib.gsx_sor_dist_local_run(_ptr(xyz_local), n_local, idx_base, n_global, world, bminp, cell, _ptr(pos4),
-                                     _ptr(cuts), _ptr(ws_l), ws_l.numel(), _stream()), "gsx_sor_dist_local_run")
+    pos4, cuts = ops.local_run(xyz_local, idx_base, n_global, world, bmin, cell)
     send = (cuts[1:] - cuts[:-1]).contiguous()
     recv = torch.empty_like(send)
     dist.all_to_all_single(recv, send, group=group)
@@ -201,36 +247,29 @@ def build_grid_distributed(xyz_local: torch.Tensor, group=None):
     m = sum(recv_l)
     pos4_r = torch.empty((m, 4), dtype=torch.float32, device=dev)
     dist.all_to_all_single(pos4_r, pos4, recv_l, send_l, group=group)
-    # B. owner-local sort of the received points by (bucket, in-cell Morton)
-    ws_m = ws_l if m <= n_local else sor.workspace(max(m, 1), dev)
-    ws = sor.workspace(n_global, dev)
+    # B. owner-local sort, then all-gather of the segments in owner order = the globally hash-sorted array
+    ws, spos_full = ops.new_grid_storage(n_global, dev)
     seg_sizes_t = torch.zeros(world, dtype=torch.int64, device=dev)
     seg_sizes_t[rank] = m
     dist.all_reduce(seg_sizes_t, group=group)
     seg_sizes = [int(v) for v in seg_sizes_t.tolist()]
-    off = lib.gsx_sor_spos_offset(n_global)
-    spos_full = ws[off: off + n_global * 16].view(torch.float32).view(n_global, 4)   # all-gather target in ws
     if len(set(seg_sizes)) == 1:
         seg = torch.empty((m, 4), dtype=torch.float32, device=dev)
-        check(lib.gsx_sor_dist_merge(_ptr(pos4_r), m, n_global, bminp, cell, _ptr(seg), _ptr(ws_m), ws_m.numel(),
-                                     _stream()), "gsx_sor_dist_merge")
+        ops.merge_into(pos4_r, n_global, bmin, cell, seg)
         dist.all_gather_into_tensor(spos_full, seg, group=group)
     else:
-        # ragged owners: every rank writes its segment at its global offset, the rest is zero -> all-reduce? no:
-        # broadcast segment by segment (sizes differ by at most a few buckets' worth of points)
+        # ragged owners (N not a multiple of G): every rank sorts straight into its slot, then the slots are
+        # broadcast one by one (sizes differ by at most one bucket)
         base = sum(seg_sizes[:rank])
-        seg = spos_full[base: base + m]
-        check(lib.gsx_sor_dist_merge(_ptr(pos4_r), m, n_global, bminp, cell, _ptr(seg), _ptr(ws_m), ws_m.numel(),
-                                     _stream()), "gsx_sor_dist_merge")
+        ops.merge_into(pos4_r, n_global, bmin, cell, spos_full[base: base + m])
         o = 0
         for r, sz in enumerate(seg_sizes):
             if sz:
-                dist.broadcast(spos_full[o: o + sz], src=dist.get_global_rank(group, r) if group else r, group=group)
+                src = dist.get_global_rank(group, r) if group is not None else r
+                dist.broadcast(spos_full[o: o + sz], src=src, group=group)
             o += sz
     # C. table, boxes, bucket boxes -- replicated, linear in n_global
-    check(lib.gsx_sor_build_from_sorted(_ptr(spos_full), n_global, bminp, cell, _ptr(ws), ws.numel(), _stream()),
-          "gsx_sor_build_from_sorted")
-    return sor.SorGrid(n_global, ws, bmin, cell), sizes
+    return ops.finish(ws, spos_full, n_global, bmin, cell), sizes
 
 
 def sor_filter_auto(xyz_local, k=25, threshold_factor=1.0, hash_mode=None, group=None, return_means=False):
@@ -240,18 +279,19 @@ def sor_filter_auto(xyz_local, k=25, threshold_factor=1.0, hash_mode=None, group
 
 
 def sor_filter_sharded_v2(xyz_local: torch.Tensor, k: int = 25, threshold_factor: float = 1.0,
-                          hash_mode: str | None = None, group=None, return_means: bool = False):
+                          hash_mode: str | None = None, group=None, return_means: bool = False, ops=None,
+                          build_ops=None):
     """Like sor_filter_sharded, with the distributed grid build (no replicated sort, no all-gather of raw xyz)."""
-    from . import sor
+    ops = ops or _GsxOps()
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    grid, sizes = build_grid_distributed(xyz_local, group)
-    n = grid.n
+    grid, sizes = build_grid_distributed(xyz_local, group, ops=build_ops)
+    n = sum(sizes)
     qb, qe = query_range(n, rank, world)
     means = torch.zeros(n, dtype=torch.float32, device=xyz_local.device)
-    sor.mean_dists(grid, k, hash_mode, out=means, q_range=(qb, qe))
+    ops.mean_dists_range(grid, k, hash_mode, means, qb, qe)
     dist.all_reduce(means, op=dist.ReduceOp.SUM, group=group)
-    mask_all = sor.threshold_mask(means, sor.mean_std(means), threshold_factor)
+    mask_all = ops.mask_from_means(means, threshold_factor)
     off = sum(sizes[:rank])
     sl = slice(off, off + sizes[rank])
     return (mask_all[sl], means[sl]) if return_means else mask_all[sl]

@@ -163,3 +163,108 @@ def test_density_sharded_equals_single():
         got = np.concatenate([res[0][key][0], res[1][key][0]])
         assert np.array_equal(got, want), key
         assert res[0][key][1]["clusters"] == info["clusters"] == res[1][key][1]["clusters"]
+
+
+class OracleBuildOps:
+    """NumPy stand-ins for the three CUDA stages of the distributed grid build (gsx.dist._GsxBuildOps)."""
+    P = (73856093, 19349663, 83492791)
+
+    def _hash(self, pos, bmin, cell, n_global):
+        gi = np.floor((pos - bmin) / np.float32(cell)).astype(np.int32).astype(np.int64)
+        return ((gi[:, 0] * self.P[0]) ^ (gi[:, 1] * self.P[1]) ^ (gi[:, 2] * self.P[2])) % n_global
+
+    def cell_size(self, mm, n_global):
+        lo, hi = mm[:3], mm[3:]
+        vol = np.prod(hi - lo)
+        if vol <= 0:
+            vol = 1.0
+        avg = max(1e-8, vol / n_global)
+        return max(float((avg * 32) ** (1.0 / 3.0)), 1e-4)
+
+    def local_run(self, xyz_local, idx_base, n_global, world, bmin, cell):
+        pos = xyz_local.numpy()
+        owner = self._hash(pos, bmin, cell, n_global) * world // n_global
+        order = np.argsort(owner, kind="stable")
+        pos4 = np.empty((len(pos), 4), np.float32)
+        pos4[:, :3] = pos[order]
+        pos4[:, 3] = (idx_base + order).astype(np.int32).view(np.float32)
+        cuts = np.searchsorted(owner[order], np.arange(world + 1))
+        return torch.from_numpy(pos4), torch.from_numpy(cuts.astype(np.int64))
+
+    def merge_into(self, pos4_r, n_global, bmin, cell, out):
+        p = pos4_r.numpy()
+        order = np.argsort(self._hash(p[:, :3], bmin, cell, n_global), kind="stable")
+        out.copy_(torch.from_numpy(p[order]))
+
+    def new_grid_storage(self, n_global, dev):
+        return None, torch.empty((n_global, 4), dtype=torch.float32)
+
+    def finish(self, ws, spos_full, n_global, bmin, cell):
+        return dict(spos=spos_full.numpy().copy(), bmin=bmin, cell=cell, n=n_global)
+
+
+class OracleQueryOps(OracleOps):
+    def mean_dists_range(self, grid, k, hash_mode, out, qb, qe):
+        import ctypes
+        import oracle
+        from oracle import _p
+        n = grid["n"]
+        sp = np.ascontiguousarray(grid["spos"][:, :3])
+        orig = grid["spos"][:, 3].copy().view(np.int32)
+        h = OracleBuildOps()._hash(sp, grid["bmin"], grid["cell"], n).astype(np.int32)
+        assert np.all(h[1:] >= h[:-1])                       # the all-gathered array is globally hash-sorted
+        uniq, first, cnt = np.unique(h, return_index=True, return_counts=True)
+        cs = np.full(n, -1, np.int32)
+        cc = np.zeros(n, np.int32)
+        cs[uniq], cc[uniq] = first, cnt
+        md = np.zeros(n, np.float32)
+        b = grid["bmin"]
+        oracle.lib().orc_sor_mean_dists(_p(sp, ctypes.c_float), _p(cs, ctypes.c_int32), _p(cc, ctypes.c_int32),
+                                        _p(md, ctypes.c_float), float(b[0]), float(b[1]), float(b[2]),
+                                        ctypes.c_float(grid["cell"]), n, n, min(k, 50),
+                                        {"i32wrap": 0, "i64": 1}[hash_mode or "i32wrap"], None)
+        out.numpy()[orig[qb:qe]] = md[qb:qe]
+
+
+def _dist_build_worker(rank, world, port, sizes, q):
+    sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "3dgsconverter_b200"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gsx import dist as gd, synth
+    xyz = synth.xyz(sum(sizes), "mixed")
+    off = sum(sizes[:rank])
+    local = torch.from_numpy(xyz[off:off + sizes[rank]].copy())
+    mask, means = gd.sor_filter_sharded_v2(local, 16, 2.0, "i64", return_means=True, ops=OracleQueryOps(),
+                                           build_ops=OracleBuildOps())
+    q.put((rank, mask.numpy(), means.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("sizes", [(15_000, 15_000), (20_000, 9_999), (7_000, 7_000, 7_001)])
+def test_distributed_build_driver_equals_single(sizes):
+    """The host logic of gsx.dist.build_grid_distributed / sor_filter_sharded_v2 (owner partition, all-to-all with
+    split lists, equal and ragged all-gather, query ranges) with NumPy stages: bit-identical to the oracle."""
+    import oracle
+    from gsx import synth
+    world = len(sizes)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 35500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_dist_build_worker, args=(r, world, port, sizes, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = {}
+    for _ in range(world):
+        r, m, md = q.get(timeout=300)
+        res[r] = (m, md)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    xyz = synth.xyz(sum(sizes), "mixed")
+    want = oracle.sor_taichi_mean_dists(xyz, 16, "i64")
+    got = np.concatenate([res[r][1] for r in range(world)])
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(np.concatenate([res[r][0] for r in range(world)]), oracle.threshold_mask(want, 2.0))

@@ -106,3 +106,29 @@ def test_dropin_mirror_has_reference_surface():
     assert np.array_equal(C, X) and np.array_equal(L, np.arange(4, dtype=np.int32))
     C, L = gpu_ops.kmeans(np.random.default_rng(0).random((200, 3)).astype(np.float32), 4, use_gpu=False)
     assert C.shape == (4, 3) and L.shape == (200,)
+
+
+def test_build_ops_glue_reaches_the_library(gsx_lib, monkeypatch):
+    """CPU: the ctypes glue of gsx.dist._GsxBuildOps is well-formed -- without a GPU every stage gets as far as the
+    CUDA launch inside libgsx and fails there with GsxError (not with a Python-level error)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("meant for the CPU box")
+    import ctypes
+    from gsx import GsxError, sor
+    from gsx.dist import _GsxBuildOps
+    monkeypatch.setattr(sor, "_stream", lambda: ctypes.c_void_p(0))   # torch has no CUDA stream on this box
+    ops = _GsxBuildOps()
+    mm = np.array([0, 0, 0, 1, 2, 3], np.float32)
+    cell = ops.cell_size(mm, 1000)
+    assert cell == pytest.approx(float((np.float32(6.0) / 1000 * 32) ** (1.0 / 3.0)), rel=1e-6)
+    xyz = torch.rand((1000, 3))
+    bmin = mm[:3].copy()
+    with pytest.raises(GsxError):
+        ops.local_run(xyz, 0, 1000, 2, bmin, cell)
+    with pytest.raises(GsxError):
+        ops.merge_into(torch.rand((1000, 4)), 1000, bmin, cell, torch.empty((1000, 4)))
+    ws, spos = ops.new_grid_storage(1000, torch.device("cpu"))
+    assert spos.shape == (1000, 4) and spos.data_ptr() >= ws.data_ptr()
+    with pytest.raises(GsxError):
+        ops.finish(ws, spos, 1000, bmin, cell)
