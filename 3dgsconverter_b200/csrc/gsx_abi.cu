@@ -399,18 +399,22 @@ int64_t gsx_kmeans_workspace_bytes(int64_t n_total, int32_t nprob, int32_t K, in
     return kmeans_workspace_bytes(n_total, nprob, K, D);
 }
 
-void gsx_kmeans_set_prefilter(int32_t on) { kmeans_set_prefilter(on); }
-int32_t gsx_kmeans_get_prefilter(void) { return kmeans_get_prefilter(); }
-
 int gsx_kmeans_lloyd_device(const float* X_dev, const int64_t* row_off_host, int32_t nprob, int32_t K, int32_t D,
                             int32_t max_iter, float* C_dev, int32_t* labels_dev, int32_t* counts_dev, void* ws,
-                            int64_t ws_bytes, void* stream) {
+                            int64_t ws_bytes, int32_t assign_mode, unsigned long long* tc_stats_dev, void* stream) {
     return kmeans_lloyd(X_dev, row_off_host, nprob, K, D, max_iter, C_dev, labels_dev, counts_dev, ws, ws_bytes,
-                        (cudaStream_t)stream);
+                        assign_mode, tc_stats_dev, (cudaStream_t)stream);
+}
+
+int32_t gsx_kmeans_tensor_core_supported(int32_t K, int32_t D) { return kmeans_tc_supported(K, D) ? 1 : 0; }
+
+int gsx_kmeans_tc_debug_scores(const float* X_dev, int64_t rows, const float* C_dev, int32_t K, int32_t D,
+                               int32_t variant, float* scores_dev, void* ws, int64_t ws_bytes, void* stream) {
+    return kmeans_tc_debug_scores(X_dev, rows, C_dev, K, D, variant, scores_dev, ws, ws_bytes, (cudaStream_t)stream);
 }
 
 int gsx_kmeans_host(const float* X_host, int64_t n, int32_t K, int32_t D, int32_t max_iter, float* C_host_inout,
-                    int32_t* labels_host) {
+                    int32_t* labels_host, int32_t assign_mode) {
     GSX_REQUIRE(n >= 1 && K >= 1 && D >= 1, GSX_ERR_ARG, "kmeans: bad shape");
     cudaStream_t st = 0;
     DevBuf X(st), C(st), L(st), cnt(st), ws(st);
@@ -425,7 +429,7 @@ int gsx_kmeans_host(const float* X_host, int64_t n, int32_t K, int32_t D, int32_
     GSX_CUDA_CHECK(cudaMemcpyAsync(C.p, C_host_inout, (size_t)K * D * 4, cudaMemcpyHostToDevice, st));
     GSX_CUDA_CHECK(cudaMemsetAsync(L.p, 0, (size_t)n * 4, st));
     int64_t off[2] = {0, n};
-    if ((rc = kmeans_lloyd((const float*)X.p, off, 1, K, D, max_iter, (float*)C.p, (int*)L.p, (int*)cnt.p, ws.p, wsb, st)))
+    if ((rc = kmeans_lloyd((const float*)X.p, off, 1, K, D, max_iter, (float*)C.p, (int*)L.p, (int*)cnt.p, ws.p, wsb, assign_mode, nullptr, st)))
         return rc;
     GSX_CUDA_CHECK(cudaMemcpyAsync(C_host_inout, C.p, (size_t)K * D * 4, cudaMemcpyDeviceToHost, st));
     GSX_CUDA_CHECK(cudaMemcpyAsync(labels_host, L.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));

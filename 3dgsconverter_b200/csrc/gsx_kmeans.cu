@@ -29,12 +29,6 @@ namespace gsx {
 constexpr int kAssignThreads = 128;
 constexpr int kCentTile = 64;  // centroids per shared-memory tile
 
-struct KmProb {
-    long long row0;  // first row of the problem in X
-    long long rows;  // number of rows
-    int tile0;       // first assign tile of the problem
-    int sub0;        // first label sub-tile (kSubTile points, one warp each) of the problem
-};
 
 constexpr int kSubTile = 1024;     // points per warp in the stable label partition
 constexpr int kMaxSortK = 2047;    // clusters (+1 overflow bin) whose per-warp counters fit shared memory
@@ -599,6 +593,7 @@ struct KmWs {
     int* totals;
     int* offs;
     float* cmax;
+    int* err;
     size_t total;
     bool ok;
 };
@@ -613,6 +608,7 @@ static KmWs km_carve(void* ws, size_t bytes, int64_t n_total, int nprob, int K, 
     w.totals = c.take<int>(sorted ? (size_t)nprob * (K + 1) : 1);
     w.offs = c.take<int>(sorted ? (size_t)nprob * (K + 1) : 1);
     w.cmax = c.take<float>((size_t)nprob + 8);
+    w.err = c.take<int>(8);
     w.total = align_up(c.off, 256);
     w.ok = c.ok();
     return w;
@@ -628,16 +624,12 @@ int64_t kmeans_workspace_bytes(int64_t n_total, int nprob, int K, int D) {
     return (int64_t)w.total + 1024;
 }
 
-static int g_prefilter = 0;
-void kmeans_set_prefilter(int on) { g_prefilter = on ? 1 : 0; }
-int kmeans_get_prefilter() { return g_prefilter; }
-
 template <int D>
 static void launch_assign(const float* X, const float* C, int* labels, const KmProb* probs, int nprob, int K,
-                          int tiles, const float* cmax, cudaStream_t st) {
+                          int tiles, const float* cmax, bool prefilter, cudaStream_t st) {
     constexpr int P = PointsPerThread<D>::value;
     if constexpr (D >= 9) {
-        if (g_prefilter && cmax) {
+        if (prefilter && cmax) {
             k_kmeans_cmax<<<nprob, 256, 0, st>>>(C, K, D, const_cast<float*>(cmax));
             count_launch();
             k_kmeans_assign_pre<D, P><<<tiles, kAssignThreads, 0, st>>>(X, C, labels, probs, nprob, K, cmax);
@@ -661,7 +653,14 @@ static int points_per_thread(int D) {
 }
 
 int kmeans_lloyd(const float* X, const int64_t* row_off, int nprob, int K, int D, int max_iter, float* C, int* labels,
-                 int* counts, void* ws, int64_t ws_bytes, cudaStream_t st) {
+                 int* counts, void* ws, int64_t ws_bytes, int assign_mode, unsigned long long* tc_stats,
+                 cudaStream_t st) {
+    GSX_REQUIRE(assign_mode >= 0 && assign_mode <= 3, GSX_ERR_ARG, "kmeans: bad assign_mode %d", assign_mode);
+    if (assign_mode == GSX_KM_ASSIGN_TENSOR)
+        GSX_REQUIRE(kmeans_tc_supported(K, D), GSX_ERR_UNSUPPORTED,
+                    "kmeans: tensor-core assign needs D in {9,24,45} and K <= 256 (got K=%d D=%d)", K, D);
+    const bool use_tc = assign_mode == GSX_KM_ASSIGN_TENSOR || (assign_mode == GSX_KM_ASSIGN_AUTO && kmeans_tc_supported(K, D));
+    const bool prefilter = assign_mode == GSX_KM_ASSIGN_FMA_PREFILTER;
     GSX_REQUIRE(nprob >= 1 && K >= 1 && D >= 1 && max_iter >= 0, GSX_ERR_ARG, "kmeans: bad shape");
     const int64_t n_total = row_off[nprob] - row_off[0];
     GSX_REQUIRE(row_off[0] == 0, GSX_ERR_ARG, "kmeans: row_off[0] must be 0");
@@ -669,7 +668,7 @@ int kmeans_lloyd(const float* X, const int64_t* row_off, int nprob, int K, int D
                 "kmeans: workspace too small");
     const int per_tile = kAssignThreads * points_per_thread(D);
     std::vector<KmProb> hp(nprob);
-    long long tiles = 0, nsub = 0;
+    long long tiles = 0, nsub = 0, tc_tiles = 0;
     for (int p = 0; p < nprob; ++p) {
         hp[p].row0 = row_off[p];
         hp[p].rows = row_off[p + 1] - row_off[p];
@@ -677,6 +676,8 @@ int kmeans_lloyd(const float* X, const int64_t* row_off, int nprob, int K, int D
         GSX_REQUIRE(hp[p].rows < 2147483647ll, GSX_ERR_UNSUPPORTED, "kmeans: problem %d has too many rows", p);
         hp[p].tile0 = (int)tiles;
         hp[p].sub0 = (int)nsub;
+        hp[p].tc_tile0 = tc_tiles;
+        tc_tiles += (hp[p].rows + 127) / 128;
         tiles += (hp[p].rows + per_tile - 1) / per_tile;
         nsub += (hp[p].rows + kSubTile - 1) / kSubTile;
     }
@@ -695,15 +696,21 @@ int kmeans_lloyd(const float* X, const int64_t* row_off, int nprob, int K, int D
         GSX_CUDA_CHECK(cudaFuncSetAttribute(k_km_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         GSX_CUDA_CHECK(cudaFuncSetAttribute(k_km_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
+    if (use_tc) GSX_CUDA_CHECK(cudaMemsetAsync(w.err, 0, sizeof(int), st));
     for (int it = 0; it < max_iter; ++it) {
+        if (use_tc) {
+            int rc = kmeans_assign_tc(X, (long long)n_total * D, C, labels, dp, nprob, K, D, tc_tiles, 0, 0, nullptr,
+                                      tc_stats, w.err, st);
+            if (rc) return rc;
+        } else
         switch (D) {
-            case 1: launch_assign<1>(X, C, labels, dp, nprob, K, (int)tiles, w.cmax, st); break;
-            case 2: launch_assign<2>(X, C, labels, dp, nprob, K, (int)tiles, w.cmax, st); break;
-            case 3: launch_assign<3>(X, C, labels, dp, nprob, K, (int)tiles, w.cmax, st); break;
-            case 4: launch_assign<4>(X, C, labels, dp, nprob, K, (int)tiles, w.cmax, st); break;
-            case 9: launch_assign<9>(X, C, labels, dp, nprob, K, (int)tiles, w.cmax, st); break;
-            case 24: launch_assign<24>(X, C, labels, dp, nprob, K, (int)tiles, w.cmax, st); break;
-            case 45: launch_assign<45>(X, C, labels, dp, nprob, K, (int)tiles, w.cmax, st); break;
+            case 1: launch_assign<1>(X, C, labels, dp, nprob, K, (int)tiles, w.cmax, prefilter, st); break;
+            case 2: launch_assign<2>(X, C, labels, dp, nprob, K, (int)tiles, w.cmax, prefilter, st); break;
+            case 3: launch_assign<3>(X, C, labels, dp, nprob, K, (int)tiles, w.cmax, prefilter, st); break;
+            case 4: launch_assign<4>(X, C, labels, dp, nprob, K, (int)tiles, w.cmax, prefilter, st); break;
+            case 9: launch_assign<9>(X, C, labels, dp, nprob, K, (int)tiles, w.cmax, prefilter, st); break;
+            case 24: launch_assign<24>(X, C, labels, dp, nprob, K, (int)tiles, w.cmax, prefilter, st); break;
+            case 45: launch_assign<45>(X, C, labels, dp, nprob, K, (int)tiles, w.cmax, prefilter, st); break;
             default:
                 k_kmeans_assign_generic<<<(int)tiles, kAssignThreads, 0, st>>>(X, C, labels, dp, nprob, K, D);
         }
@@ -725,6 +732,35 @@ int kmeans_lloyd(const float* X, const int64_t* row_off, int nprob, int K, int D
         k_km_accum<<<ublocks, 256, 0, st>>>(X, C, w.member, w.offs, counts, dp, nprob, K, D);
         GSX_KERNEL_CHECK();
     }
+    if (use_tc && max_iter > 0) {  // a timed-out mbarrier wait inside the tensor-core kernel (protocol bug) is an error
+        int herr = 0;
+        GSX_CUDA_CHECK(cudaMemcpyAsync(&herr, w.err, sizeof(int), cudaMemcpyDeviceToHost, st));
+        GSX_CUDA_CHECK(cudaStreamSynchronize(st));
+        GSX_REQUIRE(herr == 0, GSX_ERR_CUDA, "kmeans: tensor-core assign kernel timed out on an mbarrier");
+    }
+    return GSX_OK;
+}
+
+// debug / test hook: raw tensor-core scores of the first 128 rows against K centroids (one problem)
+int kmeans_tc_debug_scores(const float* X, int64_t rows, const float* C, int K, int D, int variant, float* scores,
+                           void* ws, int64_t ws_bytes, cudaStream_t st) {
+    GSX_REQUIRE(kmeans_tc_supported(K, D) && rows >= 1, GSX_ERR_UNSUPPORTED, "kmeans_tc_debug: unsupported shape");
+    GSX_REQUIRE(ws_bytes >= 1024, GSX_ERR_WORKSPACE, "kmeans_tc_debug: workspace too small");
+    KmProb hp;
+    hp.row0 = 0, hp.rows = rows, hp.tile0 = 0, hp.sub0 = 0, hp.tc_tile0 = 0;
+    KmProb* dp = reinterpret_cast<KmProb*>(ws);
+    int* err = reinterpret_cast<int*>(reinterpret_cast<char*>(ws) + 512);
+    GSX_CUDA_CHECK(cudaMemcpyAsync(dp, &hp, sizeof(hp), cudaMemcpyHostToDevice, st));
+    GSX_CUDA_CHECK(cudaMemsetAsync(err, 0, sizeof(int), st));
+    GSX_CUDA_CHECK(cudaStreamSynchronize(st));
+    int rc = kmeans_assign_tc(X, (long long)rows * D, C, nullptr, dp, 1, K, D, (rows + 127) / 128, variant, 1, scores,
+                              nullptr, err, st);
+    if (rc) return rc;
+    GSX_KERNEL_CHECK();
+    int herr = 0;
+    GSX_CUDA_CHECK(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    GSX_CUDA_CHECK(cudaStreamSynchronize(st));
+    GSX_REQUIRE(herr == 0, GSX_ERR_CUDA, "kmeans_tc_debug: mbarrier wait timed out");
     return GSX_OK;
 }
 

@@ -1,0 +1,460 @@
+// gsx_kmeans_tc.cu -- K-Means assign step on the 5th-gen tensor cores (tcgen05 + TMEM), sm_100a.
+//
+// Replaces gpu_ops.py:57-73 (k_means_assign) with bit-identical labels.  The contract is a strict
+// float32 (sub, mul, add -- no fma, dims ascending) distance per (point, centroid), lowest index winning ties;
+// that rounding sequence is not a GEMM.  What IS a GEMM is the score
+//        s_c = x . c - 0.5 ||c||^2            (E_c = ||x||^2 - 2 s_c is the squared distance),
+// so the kernel
+//   1. computes S = [X | 1 1 1] . [C | b_hi b_mid b_lo]^T  for a tile of 128 points x (up to) 256 centroids with
+//      tcgen05.mma.kind::tf32 (A = the points, B = the centroids, both K-major in shared memory, the accumulator
+//      128 lanes x 256 columns of TMEM); the bias -0.5||c||^2 is split into three TF32-exact pieces and rides in
+//      three padding columns of the K dimension, so the bias costs nothing and adds no rounding;
+//   2. reads the scores back with tcgen05.ld (thread r <-> TMEM lane r <-> point r), takes the row maximum and
+//      builds the set of centroids whose score is within a rounding-error margin M of it;
+//   3. evaluates the strict contract distance only for those candidates (one candidate: it IS the answer, no
+//      evaluation at all), ascending index, strict '<'.
+// Margin: with |s~_c - t_c| <= eta for every centroid (t_c the real-arithmetic score, s~_c what
+// the tensor core returns) and |a_c - E_c| <= g E_c for the strict float32 distance a_c, the contract's answer
+// c* satisfies  s~_{c*} >= s~_max - (2 eta + g/(1-g) E_{c'}),  E_{c'} <= ||x||^2 - 2 s~_max + 2 eta.
+// eta covers the TF32 conversion of both operands (relative 2^-10 each, truncation or rounding), the tensor
+// core's float32 accumulation and the float32 evaluation of the bias; the kernel uses twice the proven bound.
+// Anything non-finite, or an empty candidate set, falls back to the full strict scan inside the same kernel, so
+// the labels are bit-identical to k_kmeans_assign in every case (tests/test_kmeans_tc_gpu.py).
+//
+// Data movement: a tile is 128 consecutive rows of X = 128*D*4 contiguous bytes; one elected thread moves it
+// global -> shared with a 1-D TMA bulk copy (cp.async.bulk, completion on an mbarrier) one tile ahead of the
+// MMA, then every thread re-lays its own row into the UMMA canonical layout (conflict-free for odd D).
+#include "gsx_common.cuh"
+#include "gsx_kmeans.cuh"
+
+namespace gsx {
+
+#define GSX_FULL 0xffffffffu
+
+constexpr int kTcThreads = 128;   // one thread per point row == one TMEM lane
+constexpr int kTcRows = 128;      // UMMA M
+constexpr int kTcMaxN = 256;      // UMMA N limit == max centroids of the tensor-core path
+constexpr unsigned kSpinLimit = 1u << 26;  // bounded mbarrier waits: a protocol bug must not hang the GPU
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// returns false on timeout
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (unsigned spin = 0; spin < kSpinLimit; ++spin) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot_smem, uint32_t ncols) {  // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot_smem)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_free(uint32_t taddr, uint32_t ncols) {  // the same warp
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): core matrix = 8 rows x 16 B,
+// lbo = byte distance of the two core matrices that are adjacent in K, sbo = byte distance of 8-row groups.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+           (1ull << 46);
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, TF32 inputs, float32 accumulate; issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// 32 consecutive float32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+        "%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float tf32_trunc(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+// byte offset of element (row, k) of a K-major operand with KP (multiple of 8) padded K columns
+template <int KP>
+__device__ __forceinline__ uint32_t op_off(int row, int k) {
+    return (uint32_t)((row >> 3) * (KP / 4) * 128 + (k >> 2) * 128 + (row & 7) * 16 + (k & 3) * 4);
+}
+
+struct TcShared {  // tail of the dynamic shared memory (after the operand tiles and the staging buffer)
+    uint64_t bar_copy;
+    uint64_t bar_mma;
+    uint32_t tmem_base;
+    float cmax;
+    float red[4];
+};
+
+// mode 0: labels; mode 1 (debug): dump the raw scores of the first tile to dump[128*npad] and return
+template <int D, int KP>
+__global__ void __launch_bounds__(kTcThreads)
+    k_km_assign_tc(const float* __restrict__ X, long long x_floats, const float* __restrict__ C,
+                   int* __restrict__ labels, const KmProb* __restrict__ probs, int nprob, int K, int npad,
+                   int tmem_cols, long long tiles_total, int desc_variant, int mode, float* __restrict__ dump,
+                   unsigned long long* __restrict__ tc_stats, int* __restrict__ err_flag) {
+    static_assert(KP % 8 == 0 && KP >= D + 3, "K padding");
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* sB = smem;                                   // [kTcMaxN x KP] float32, UMMA K-major layout
+    unsigned char* sA = sB + kTcMaxN * KP * 4;                  // [128 x KP]
+    float* sStage = reinterpret_cast<float*>(sA + kTcRows * KP * 4);  // 128*D floats + 8 (alignment slack)
+    TcShared* sh = reinterpret_cast<TcShared*>(reinterpret_cast<unsigned char*>(sStage) + (kTcRows * D + 8) * 4);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        mbar_init(&sh->bar_copy, 1);
+        mbar_init(&sh->bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(&sh->tmem_base, (uint32_t)tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sh->tmem_base;
+
+    const long long t0 = tiles_total * (long long)blockIdx.x / gridDim.x;
+    const long long t1 = tiles_total * (long long)(blockIdx.x + 1) / gridDim.x;
+    const bool x_aligned = (reinterpret_cast<uintptr_t>(X) & 15) == 0;
+    const uint32_t lbo = desc_variant == 1 ? (uint32_t)(KP / 4) * 128u : 128u;
+    const uint32_t sbo = desc_variant == 1 ? 128u : (uint32_t)(KP / 4) * 128u;
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(npad >> 3) << 17) | ((kTcRows >> 4) << 24);
+    constexpr float kU = 5.9604645e-8f;                        // 2^-24
+    constexpr float kGs = 2.f * (D + 3) * kU * 1.02f;          // >= 2 gamma_{D+2} / (1 - gamma_{D+2})
+    constexpr float kEpsIn = 1.953125e-3f * 1.01f;             // 2^-9 (+): two TF32 conversions, 2^-10 each
+    constexpr float kEpsAcc = 3.0517578e-5f;                   // 2^-15: accumulation + bias evaluation slack
+
+    // geometry of tile t: problem, first row, rows, and whether the bulk copy may be used
+    struct TileGeo { int p; long long row0; int rows; long long off_floats; bool bulk; uint32_t pre, bytes; };
+    auto geo = [&](long long t) {
+        TileGeo g;
+        int lo = 0, hi = nprob - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (probs[mid].tc_tile0 <= t) lo = mid; else hi = mid - 1;
+        }
+        g.p = lo;
+        const long long lt = t - probs[lo].tc_tile0;
+        const long long left = probs[lo].rows - lt * kTcRows;
+        g.rows = left < kTcRows ? (int)left : kTcRows;
+        g.row0 = probs[lo].row0 + lt * kTcRows;
+        g.off_floats = g.row0 * D;
+        const long long ob = g.off_floats * 4;
+        g.pre = (uint32_t)(ob & 15);
+        g.bytes = (g.pre + (uint32_t)g.rows * D * 4 + 15u) & ~15u;
+        g.bulk = x_aligned && ((ob - g.pre) + g.bytes <= x_floats * 4);
+        return g;
+    };
+
+    uint32_t copy_phase = 0, mma_phase = 0;
+    bool failed = false;
+    TileGeo cur{};
+    if (t0 < t1) {
+        cur = geo(t0);
+        if (tid == 0 && cur.bulk) {
+            mbar_expect_tx(&sh->bar_copy, cur.bytes);
+            bulk_g2s(sStage, reinterpret_cast<const char*>(X) + (cur.off_floats * 4 - cur.pre), cur.bytes, &sh->bar_copy);
+        }
+    }
+    int cur_prob = -1;
+    float Cm = 0.f;
+    unsigned long long st_strict = 0, st_multi = 0, st_full = 0;
+
+    for (long long t = t0; t < t1 && !failed; ++t) {
+        const TileGeo g = cur;
+        const float* Cp = C + (size_t)g.p * K * D;
+        if (g.p != cur_prob) {  // (re)load the centroids of this problem as the B operand
+            __syncthreads();    // nobody is still reading sB in a strict evaluation of the previous tile
+            for (int idx = tid; idx < npad * (KP / 4); idx += kTcThreads) {
+                const int c = idx / (KP / 4), j = idx - c * (KP / 4);
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int k = 4 * j + e;
+                    v[e] = (c < K && k < D) ? __ldg(Cp + (size_t)c * D + k) : 0.f;
+                }
+                *reinterpret_cast<float4*>(sB + op_off<KP>(c, 4 * j)) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+            __syncthreads();
+            float mx = 0.f;
+            for (int c = tid; c < npad; c += kTcThreads) {
+                float cn = 0.f;
+                if (c < K) {
+                    for (int k = 0; k < D; ++k) {
+                        const float v = *reinterpret_cast<const float*>(sB + op_off<KP>(c, k));
+                        cn = __fmaf_rn(v, v, cn);
+                    }
+                }
+                mx = fmaxf(mx, cn);
+                // bias = -0.5||c||^2 as three TF32-exact pieces; padding centroids get a huge negative score
+                const float b = c < K ? -0.5f * cn : -3.0e38f;
+                const float bh = tf32_trunc(b);
+                const float r1 = c < K ? b - bh : 0.f;       // exact (Sterbenz-like: same exponent range)
+                const float bm = tf32_trunc(r1);
+                const float bl = c < K ? r1 - bm : 0.f;      // <= 2 significant bits left: TF32-exact
+                *reinterpret_cast<float*>(sB + op_off<KP>(c, D)) = bh;
+                *reinterpret_cast<float*>(sB + op_off<KP>(c, D + 1)) = bm;
+                *reinterpret_cast<float*>(sB + op_off<KP>(c, D + 2)) = bl;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(GSX_FULL, mx, o));
+            if (lane == 0) sh->red[warp] = mx;
+            __syncthreads();
+            mx = fmaxf(fmaxf(sh->red[0], sh->red[1]), fmaxf(sh->red[2], sh->red[3]));
+            Cm = sqrtf(mx) * 1.0001f;  // inf/NaN propagate into the margin -> full strict scan below
+            cur_prob = g.p;
+        }
+
+        // ---- this thread's row: staging (bulk copy) or global -> UMMA layout, ||x||^2 on the way
+        if (g.bulk) {
+            if (!mbar_wait(&sh->bar_copy, copy_phase)) failed = true;
+            copy_phase ^= 1;
+        }
+        const bool live = tid < g.rows;
+        float xn = 0.f;
+        {
+            const float* src = g.bulk ? sStage + (g.pre >> 2) + tid * D : X + g.off_floats + (long long)tid * D;
+#pragma unroll
+            for (int j = 0; j < KP / 4; ++j) {
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int k = 4 * j + e;
+                    if (k < D) {
+                        v[e] = live ? src[k] : 0.f;
+                        xn = __fmaf_rn(v[e], v[e], xn);
+                    } else {
+                        v[e] = k < D + 3 ? 1.0f : 0.f;
+                    }
+                }
+                *reinterpret_cast<float4*>(sA + op_off<KP>(tid, 4 * j)) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+        }
+        fence_proxy_async();   // generic-proxy writes of sA / sB -> visible to the tensor core (async proxy)
+        tc_fence_before();     // this thread's tcgen05.ld of the previous tile are done before the next MMA
+        __syncthreads();
+        if (t + 1 < t1) cur = geo(t + 1);
+        if (tid == 0) {
+            tc_fence_after();
+            if (t + 1 < t1 && cur.bulk) {  // staging is free: every thread has copied its row out
+                mbar_expect_tx(&sh->bar_copy, cur.bytes);
+                bulk_g2s(sStage, reinterpret_cast<const char*>(X) + (cur.off_floats * 4 - cur.pre), cur.bytes,
+                         &sh->bar_copy);
+            }
+            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+#pragma unroll
+            for (int j = 0; j < KP / 8; ++j) {  // one instruction = 8 TF32 along K = two core matrices
+                const uint32_t koff = (uint32_t)j * 256u;  // two 128-byte core matrices further along K
+                umma_tf32(tmem_base, umma_desc(a0 + koff, lbo, sbo), umma_desc(b0 + koff, lbo, sbo), idesc, j > 0);
+            }
+            umma_commit(&sh->bar_mma);
+        }
+        if (!mbar_wait(&sh->bar_mma, mma_phase)) failed = true;
+        mma_phase ^= 1;
+        tc_fence_after();
+        if (failed) break;
+
+        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        if (mode == 1) {  // debug: raw scores of the tile
+            for (int c0 = 0; c0 < npad; c0 += 32) {
+                float v[32];
+                tmem_ld32(taddr + c0, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) dump[(size_t)tid * npad + c0 + i] = v[i];
+            }
+            break;
+        }
+
+        // ---- epilogue: row maximum, candidate mask, strict evaluation of the candidates
+        float smax = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < kTcMaxN / 32; ++w) {
+            if (w * 32 < npad) {
+                float v[32];
+                tmem_ld32(taddr + w * 32, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) smax = fmaxf(smax, v[i]);
+            }
+        }
+        const float xnu = xn * 1.0001f;
+        const float xnorm = sqrtf(xnu) * 1.0001f;
+        const float eta = (kEpsIn * xnorm * Cm + kEpsAcc * (xnorm * Cm + Cm * Cm)) * 1.5f + 1e-37f;
+        const float e_ub = fmaxf(xnu - 2.f * smax + 2.f * eta, 0.f);
+        const float marg = 2.f * eta + kGs * e_ub;
+        const float thr = smax - marg;
+        uint32_t mask[kTcMaxN / 32];
+        int cnt = 0;
+#pragma unroll
+        for (int w = 0; w < kTcMaxN / 32; ++w) {
+            mask[w] = 0;
+            if (w * 32 < npad) {
+                float v[32];
+                tmem_ld32(taddr + w * 32, v);
+                uint32_t m = 0;
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (v[i] >= thr) m |= 1u << i;
+                mask[w] = m;
+                cnt += __popc(m);
+            }
+        }
+        // the shortcut is only legal when the margin is finite, a real centroid scored, and the strict distance
+        // of the winner cannot reach the contract's 1e20 "no label" sentinel
+        const bool bad = !(marg < 3.0e38f) || !(smax > -1.0e30f) || !(e_ub < 1.0e19f) || cnt == 0;
+        int label = -1;
+        if (!bad && cnt == 1) {
+#pragma unroll
+            for (int w = 0; w < kTcMaxN / 32; ++w)
+                if (mask[w]) label = w * 32 + __ffs(mask[w]) - 1;
+        }
+        const bool need = live && (bad || cnt > 1);
+        if (__any_sync(GSX_FULL, need)) {
+            if (bad) {  // full strict scan over the real centroids
+#pragma unroll
+                for (int w = 0; w < kTcMaxN / 32; ++w) {
+                    const int left = K - w * 32;
+                    mask[w] = left >= 32 ? 0xffffffffu : (left > 0 ? (1u << left) - 1u : 0u);
+                }
+            }
+            float best = 1e20f;
+            int bk = -1;
+            if (need) {
+                ++st_multi;
+                if (bad) ++st_full;
+            }
+            for (;;) {
+                int c = -1;
+                if (need) {
+#pragma unroll
+                    for (int w = kTcMaxN / 32 - 1; w >= 0; --w)
+                        if (mask[w]) c = w * 32 + __ffs(mask[w]) - 1;
+                }
+                if (!__any_sync(GSX_FULL, c >= 0)) break;
+                if (c >= 0) {
+#pragma unroll
+                    for (int w = 0; w < kTcMaxN / 32; ++w)
+                        if ((c >> 5) == w) mask[w] &= mask[w] - 1;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < (D + 3) / 4; ++j) {
+                        const float4 xv = *reinterpret_cast<const float4*>(sA + op_off<KP>(tid, 4 * j));
+                        const float4 cv = *reinterpret_cast<const float4*>(sB + op_off<KP>(c, 4 * j));
+                        const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, ca[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (4 * j + e < D) {
+                                const float df = __fsub_rn(xa[e], ca[e]);
+                                acc = __fadd_rn(acc, __fmul_rn(df, df));
+                            }
+                    }
+                    ++st_strict;
+                    if (acc < best) best = acc, bk = c;
+                }
+            }
+            if (need) label = bk;
+        }
+        if (live) labels[g.row0 + tid] = label;
+    }
+
+    if (failed && err_flag) atomicExch(err_flag, 1);
+    if (tc_stats) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            st_strict += __shfl_xor_sync(GSX_FULL, st_strict, o);
+            st_multi += __shfl_xor_sync(GSX_FULL, st_multi, o);
+            st_full += __shfl_xor_sync(GSX_FULL, st_full, o);
+        }
+        if (lane == 0) {
+            atomicAdd(tc_stats + 0, st_strict);
+            atomicAdd(tc_stats + 1, st_multi);
+            atomicAdd(tc_stats + 2, st_full);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_free(tmem_base, (uint32_t)tmem_cols);
+}
+
+template <int D, int KP>
+static int launch_tc(const float* X, long long x_floats, const float* C, int* labels, const KmProb* probs, int nprob,
+                     int K, long long tiles, int variant, int mode, float* dump, unsigned long long* stats, int* err,
+                     cudaStream_t st) {
+    const int npad = (K + 31) / 32 * 32;
+    int cols = 32;
+    while (cols < npad) cols <<= 1;
+    const size_t smem = (size_t)(kTcMaxN + kTcRows) * KP * 4 + (size_t)(kTcRows * D + 8) * 4 + sizeof(TcShared) + 64;
+    static bool attr_done = false;
+    if (!attr_done) {
+        GSX_CUDA_CHECK(cudaFuncSetAttribute(k_km_assign_tc<D, KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    long long grid = (long long)sm_count() * 2;  // two CTAs per SM: 2 x 256 TMEM columns, 2 x ~97 KB shared memory
+    if (grid > tiles) grid = tiles;
+    if (mode == 1) grid = 1;
+    if (grid < 1) grid = 1;
+    k_km_assign_tc<D, KP><<<(int)grid, kTcThreads, smem, st>>>(X, x_floats, C, labels, probs, nprob, K, npad, cols, tiles,
+                                                               variant, mode, dump, stats, err);
+    return GSX_OK;
+}
+
+bool kmeans_tc_supported(int K, int D) { return (D == 9 || D == 24 || D == 45) && K >= 1 && K <= kTcMaxN; }
+
+int kmeans_assign_tc(const float* X, long long x_floats, const float* C, int* labels, const KmProb* probs_dev, int nprob,
+                     int K, int D, long long tiles, int variant, int mode, float* dump, unsigned long long* stats,
+                     int* err_flag_dev, cudaStream_t st) {
+    switch (D) {
+        case 9: return launch_tc<9, 16>(X, x_floats, C, labels, probs_dev, nprob, K, tiles, variant, mode, dump, stats, err_flag_dev, st);
+        case 24: return launch_tc<24, 32>(X, x_floats, C, labels, probs_dev, nprob, K, tiles, variant, mode, dump, stats, err_flag_dev, st);
+        case 45: return launch_tc<45, 48>(X, x_floats, C, labels, probs_dev, nprob, K, tiles, variant, mode, dump, stats, err_flag_dev, st);
+        default: set_error("kmeans_tc: unsupported D=%d", D); return GSX_ERR_UNSUPPORTED;
+    }
+}
+
+}  // namespace gsx

@@ -11,7 +11,7 @@
 //     kernel) -> {start,end} bucket table -> bounding boxes of every aligned run of 32
 //     ("chunk") and 1024 ("super") sorted points.
 //   * query kernel: one warp per query, persistent CTAs with a dynamic batch counter.
-//     Lane p<27 evaluates probe p's hash and loads its 32-byte bucket entry {start, end, box};
+//     Lane p<27 evaluates probe p's hash and loads its bucket entry ({start,end}, and the 32-byte box if non-empty);
 //     the probes are visited nearest box first (redux.min on the lower bound) and dropped once
 //     lb >= tau; candidates are streamed 32 at a time with one coalesced float4 load per lane;
 //     the K best d^2 live one per lane in a register (two for K>32) and are maintained with
@@ -67,7 +67,9 @@ SorWs sor_carve(void* ws, int64_t ws_bytes, int64_t n, size_t sort_ws_bytes) {
     w.vals0 = c.take<int32_t>(n);
     w.vals1 = c.take<int32_t>(n);
     w.spos = c.take<float4>(n);
-    w.table = c.take<float4>(2 * n);
+    w.tab_se = c.take<int2>(n);
+    w.tab_box = c.take<float4>(2 * n);
+    w.startbits = c.take<uint32_t>(nchunk);
     w.caabb = c.take<float4>(2 * nchunk);
     w.saabb = c.take<float4>(2 * nsuper);
     w.partial = c.take<float>(6 * 1024);
@@ -164,21 +166,20 @@ __device__ __forceinline__ uint32_t spread6(uint32_t v) {  // 6 bits -> every th
     return v;
 }
 
-// gpu_ops.py:216-224: gi = floor((p - min)/cell) (float32 ops), int64 hash mod n.
-__global__ void __launch_bounds__(256) k_sor_keys(const float* __restrict__ xyz, int64_t n, float bx, float by,
-                                                  float bz, float cell, uint64_t M64,
-                                                  uint64_t* __restrict__ keys, int32_t* __restrict__ vals) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float fx = __fdiv_rn(__fsub_rn(xyz[3 * i], bx), cell);
-    float fy = __fdiv_rn(__fsub_rn(xyz[3 * i + 1], by), cell);
-    float fz = __fdiv_rn(__fsub_rn(xyz[3 * i + 2], bz), cell);
-    float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
+// gpu_ops.py:216-224: gi = floor((p - min)/cell) (float32 ops), int64 hash mod n (the modulo by multiply-high:
+// M64 = floor((2^64-1)/n), q in {true q - 2 .. true q}).  *fx.. return the cell-relative coordinates.
+__device__ __forceinline__ uint32_t bucket_hash(float x, float y, float z, float bx, float by, float bz, float cell,
+                                                int64_t n, uint64_t M64, float& fx, float& fy, float& fz, float& flx,
+                                                float& fly, float& flz) {
+    fx = __fdiv_rn(__fsub_rn(x, bx), cell);
+    fy = __fdiv_rn(__fsub_rn(y, by), cell);
+    fz = __fdiv_rn(__fsub_rn(z, bz), cell);
+    flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
     int64_t gx = (int64_t)(int32_t)flx, gy = (int64_t)(int32_t)fly, gz = (int64_t)(int32_t)flz;
     int64_t hx = (gx * 73856093LL) ^ (gy * 19349663LL) ^ (gz * 83492791LL);
     int64_t h;
-    if (hx >= 0) {  // always, since gi >= 0 for points inside the bounding box: divide by multiply-high
-        uint64_t q = __umul64hi((uint64_t)hx, M64);  // M64 = floor((2^64-1)/n): q in {true q - 2 .. true q}
+    if (hx >= 0) {  // always, since gi >= 0 for points inside the bounding box
+        uint64_t q = __umul64hi((uint64_t)hx, M64);
         uint64_t r = (uint64_t)hx - q * (uint64_t)n;
         while (r >= (uint64_t)n) r -= (uint64_t)n;
         h = (int64_t)r;
@@ -186,55 +187,145 @@ __global__ void __launch_bounds__(256) k_sor_keys(const float* __restrict__ xyz,
         h = hx % n;
         if (h < 0) h += n;
     }
-    // position inside the cell, 6 bits per axis (ordering only -- never affects results)
+    return (uint32_t)h;
+}
+
+__device__ __forceinline__ uint32_t bucket_of(float x, float y, float z, float bx, float by, float bz, float cell,
+                                              int64_t n, uint64_t M64) {
+    float a, b, c, d, e, f;
+    return bucket_hash(x, y, z, bx, by, bz, cell, n, M64, a, b, c, d, e, f);
+}
+
+// sort key: bucket hash << kMortonBits | Morton code of the position inside the cell (ordering only -- the
+// in-bucket order never affects results)
+__device__ __forceinline__ uint64_t bucket_key(float x, float y, float z, float bx, float by, float bz, float cell,
+                                               int64_t n, uint64_t M64) {
+    float fx, fy, fz, flx, fly, flz;
+    const uint32_t h = bucket_hash(x, y, z, bx, by, bz, cell, n, M64, fx, fy, fz, flx, fly, flz);
     uint32_t sx = (uint32_t)fminf(kMortonMax, fmaxf(0.f, (fx - flx) * kMortonScale));
     uint32_t sy = (uint32_t)fminf(kMortonMax, fmaxf(0.f, (fy - fly) * kMortonScale));
     uint32_t sz = (uint32_t)fminf(kMortonMax, fmaxf(0.f, (fz - flz) * kMortonScale));
     uint32_t mort = (spread6(sx) << 2) | (spread6(sy) << 1) | spread6(sz);
-    keys[i] = ((uint64_t)h << kMortonBits) | (uint64_t)mort;
+    return ((uint64_t)h << kMortonBits) | (uint64_t)mort;
+}
+
+__global__ void __launch_bounds__(256) k_sor_keys(const float* __restrict__ xyz, int64_t n, float bx, float by,
+                                                  float bz, float cell, uint64_t M64,
+                                                  uint64_t* __restrict__ keys, int32_t* __restrict__ vals) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = bucket_key(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], bx, by, bz, cell, n, M64);
     vals[i] = (int32_t)i;
 }
 
-// gpu_ops.py:232-237: first index and size of every bucket.  table pre-zeroed: start == end == 0 means
-// empty (the reference's cell_start == -1 <=> cell_count == 0).  A bucket entry is 32 bytes (one DRAM
-// sector): {start, end, lo.x, lo.y | lo.z, hi.x, hi.y, hi.z}; the box is filled by k_sor_bucket_boxes.
-__global__ void __launch_bounds__(256) k_sor_table(const uint64_t* __restrict__ keys, int64_t n,
-                                                   float4* __restrict__ table) {
-    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    uint32_t h = (uint32_t)(keys[j] >> kMortonBits);
-    int* e = reinterpret_cast<int*>(table + 2 * (size_t)h);
-    if (j == 0 || (uint32_t)(keys[j - 1] >> kMortonBits) != h) e[0] = (int)j;
-    if (j == n - 1 || (uint32_t)(keys[j + 1] >> kMortonBits) != h) e[1] = (int)(j + 1);
+// gpu_ops.py:228-237 in one pass over the hash-sorted order.  One block = 1024 sorted points = one "super", one
+// warp = one "chunk" of 32.  GATHER: sorted_pos = pos[sort_order] (float4, w = original index) is produced here
+// and the bucket of a position comes from its sort key; otherwise spos is given (distributed build) and the
+// bucket is re-hashed from the position.  Outputs: {start,end} of every occupied bucket (tab_se pre-zeroed:
+// start == end == 0 <=> the reference's cell_start == -1), one bit per sorted position that starts a bucket,
+// and the bounding boxes of every chunk and super.
+template <bool GATHER>
+__global__ void __launch_bounds__(1024)
+    k_sor_finish(const float* __restrict__ xyz, const int32_t* __restrict__ order, const uint64_t* __restrict__ keys,
+                 float4* __restrict__ spos, int64_t n, float bx, float by, float bz, float cell, uint64_t M64,
+                 int2* __restrict__ tab_se, uint32_t* __restrict__ startbits, float4* __restrict__ caabb,
+                 float4* __restrict__ saabb) {
+    const int64_t j = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    const int lane = lane_id();
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    uint32_t h = 0xffffffffu;
+    auto hash_at = [&](int64_t t) -> uint32_t {
+        if (GATHER) return (uint32_t)(keys[t] >> kMortonBits);
+        const float4 q = spos[t];
+        return bucket_of(q.x, q.y, q.z, bx, by, bz, cell, n, M64);
+    };
+    if (j < n) {
+        float x, y, z;
+        if (GATHER) {
+            const int32_t idx = order[j];
+            x = xyz[3 * (int64_t)idx], y = xyz[3 * (int64_t)idx + 1], z = xyz[3 * (int64_t)idx + 2];
+            spos[j] = make_float4(x, y, z, __int_as_float(idx));
+            h = (uint32_t)(keys[j] >> kMortonBits);
+        } else {
+            const float4 p = spos[j];
+            x = p.x, y = p.y, z = p.z;
+            h = bucket_of(x, y, z, bx, by, bz, cell, n, M64);
+        }
+        lo[0] = hi[0] = x;
+        lo[1] = hi[1] = y;
+        lo[2] = hi[2] = z;
+    }
+    uint32_t hprev = __shfl_up_sync(GSX_FULL, h, 1), hnext = __shfl_down_sync(GSX_FULL, h, 1);
+    if (j < n) {
+        if (lane == 0) hprev = j > 0 ? hash_at(j - 1) : ~h;
+        if (lane == 31) hnext = j + 1 < n ? hash_at(j + 1) : ~h;
+    }
+    const bool start = j < n && (j == 0 || h != hprev);
+    const bool end = j < n && (j == n - 1 || h != hnext);
+    if (start) tab_se[h].x = (int)j;
+    if (end) tab_se[h].y = (int)(j + 1);
+    const unsigned sb = __ballot_sync(GSX_FULL, start);
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(GSX_FULL, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(GSX_FULL, hi[a], o));
+        }
+    __shared__ float sm[6][32];
+    const int w = threadIdx.x >> 5;
+    const int64_t chunk = (int64_t)blockIdx.x * 32 + w;
+    if (lane == 0) {
+        if (chunk * 32 < n) {
+            startbits[chunk] = sb;
+            caabb[2 * chunk] = make_float4(lo[0], lo[1], lo[2], hi[0]);
+            caabb[2 * chunk + 1] = make_float4(hi[1], hi[2], 0.f, 0.f);
+        }
+        for (int a = 0; a < 3; ++a) {
+            sm[a][w] = lo[a];
+            sm[3 + a][w] = hi[a];
+        }
+    }
+    __syncthreads();
+    if (w == 0) {
+        float v[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            v[a] = sm[a][lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                float t = __shfl_xor_sync(GSX_FULL, v[a], o);
+                v[a] = a < 3 ? fminf(v[a], t) : fmaxf(v[a], t);
+            }
+        }
+        if (lane == 0) {
+            saabb[2 * (int64_t)blockIdx.x] = make_float4(v[0], v[1], v[2], v[3]);
+            saabb[2 * (int64_t)blockIdx.x + 1] = make_float4(v[4], v[5], 0.f, 0.f);
+        }
+    }
 }
 
-// Bounding box of every occupied bucket (exact over its points): lets the query kernel skip whole
-// buckets whose box is farther than the current K-th best, and visit the 27 probes nearest first.
-// Each warp scans 32 consecutive sorted positions for bucket starts and reduces each bucket it finds
-// cooperatively (stride 32 over the bucket's range).
-__global__ void __launch_bounds__(256) k_sor_bucket_boxes(const uint64_t* __restrict__ keys,
-                                                          const float4* __restrict__ spos,
-                                                          const float4* __restrict__ caabb, int64_t n,
-                                                          float4* __restrict__ table) {
+// Bounding box of every occupied bucket (exact over its points): lets the query kernel skip whole buckets whose
+// box is farther than the current K-th best, and visit the 27 probes nearest first.  Each warp takes the bucket
+// starts among its 32 sorted positions (startbits) and reduces each bucket cooperatively (stride 32 over the
+// bucket's range; chunks that lie entirely inside the bucket contribute their box instead of their points).
+// tab_box[2h] = {lo.xyz, -}, tab_box[2h+1] = {hi.xyz, -}: 32 bytes = one DRAM sector per occupied bucket.
+__global__ void __launch_bounds__(256)
+    k_sor_bucket_boxes(const uint32_t* __restrict__ startbits, const float4* __restrict__ spos,
+                       const float4* __restrict__ caabb, const int2* __restrict__ tab_se, int64_t n, float bx,
+                       float by, float bz, float cell, uint64_t M64, float4* __restrict__ tab_box) {
     const int lane = lane_id();
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t h = 0;
-    bool start = false;
-    if (j < n) {
-        h = (uint32_t)(keys[j] >> kMortonBits);
-        start = j == 0 || (uint32_t)(keys[j - 1] >> kMortonBits) != h;
-    }
-    unsigned m = __ballot_sync(GSX_FULL, start);
+    const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (chunk * 32 >= n) return;
+    unsigned m = startbits[chunk];
     while (m) {
         const int src = __ffs(m) - 1;
         m &= m - 1;
-        const uint32_t hb = __shfl_sync(GSX_FULL, h, src);
-        const int64_t s = (int64_t)__shfl_sync(GSX_FULL, (int)j, src);  // n < 2^31
-        const int* e = reinterpret_cast<const int*>(table + 2 * (size_t)hb);
-        const int64_t end = e[1];
+        const int64_t s = chunk * 32 + src;
+        const float4 p0 = spos[s];
+        const uint32_t hb = bucket_of(p0.x, p0.y, p0.z, bx, by, bz, cell, n, M64);
+        const int64_t end = tab_se[hb].y;
         float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-        // chunks that lie entirely inside the bucket contribute their (already computed) box; only the
-        // ragged head and tail are reduced point by point -- keeps 10^5-point buckets cheap
         int64_t cf = (s + 31) >> 5, cl = end >> 5;  // full chunks [cf, cl)
         int64_t head_end = cf * 32, tail_begin = cl * 32;
         if (cf > cl) {  // the bucket lies inside one chunk: reduce it point by point
@@ -265,64 +356,25 @@ __global__ void __launch_bounds__(256) k_sor_bucket_boxes(const uint64_t* __rest
                 hi[a] = fmaxf(hi[a], __shfl_xor_sync(GSX_FULL, hi[a], o));
             }
         if (lane == 0) {
-            float* f = reinterpret_cast<float*>(table + 2 * (size_t)hb);
-            f[2] = lo[0], f[3] = lo[1], f[4] = lo[2], f[5] = hi[0], f[6] = hi[1], f[7] = hi[2];
+            tab_box[2 * (size_t)hb] = make_float4(lo[0], lo[1], lo[2], 0.f);
+            tab_box[2 * (size_t)hb + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
         }
     }
 }
 
-// gpu_ops.py:228: sorted_pos = pos[sort_order], as float4 with w = original index; plus the boxes.
-// One block = 1024 sorted points = one "super", one warp = one chunk.
-__global__ void __launch_bounds__(1024) k_sor_gather(const float* __restrict__ xyz, const int32_t* __restrict__ order,
-                                                     int64_t n, float4* __restrict__ spos, float4* __restrict__ caabb,
-                                                     float4* __restrict__ saabb) {
-    int64_t j = (int64_t)blockIdx.x * 1024 + threadIdx.x;
-    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    if (j < n) {
-        int32_t idx = order[j];
-        float x = xyz[3 * (int64_t)idx], y = xyz[3 * (int64_t)idx + 1], z = xyz[3 * (int64_t)idx + 2];
-        spos[j] = make_float4(x, y, z, __int_as_float(idx));
-        lo[0] = hi[0] = x;
-        lo[1] = hi[1] = y;
-        lo[2] = hi[2] = z;
-    }
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo[a] = fminf(lo[a], __shfl_xor_sync(GSX_FULL, lo[a], o));
-            hi[a] = fmaxf(hi[a], __shfl_xor_sync(GSX_FULL, hi[a], o));
-        }
-    __shared__ float sm[6][32];
-    int w = threadIdx.x >> 5;
-    int64_t chunk = (int64_t)blockIdx.x * 32 + w;
-    if (lane_id() == 0) {
-        if (chunk * 32 < n) {
-            caabb[2 * chunk] = make_float4(lo[0], lo[1], lo[2], hi[0]);
-            caabb[2 * chunk + 1] = make_float4(hi[1], hi[2], 0.f, 0.f);
-        }
-        for (int a = 0; a < 3; ++a) {
-            sm[a][w] = lo[a];
-            sm[3 + a][w] = hi[a];
-        }
-    }
-    __syncthreads();
-    if (w == 0) {
-        float v[6];
-#pragma unroll
-        for (int a = 0; a < 6; ++a) {
-            v[a] = sm[a][lane_id()];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                float t = __shfl_xor_sync(GSX_FULL, v[a], o);
-                v[a] = a < 3 ? fminf(v[a], t) : fmaxf(v[a], t);
-            }
-        }
-        if (lane_id() == 0) {
-            saabb[2 * (int64_t)blockIdx.x] = make_float4(v[0], v[1], v[2], v[3]);
-            saabb[2 * (int64_t)blockIdx.x + 1] = make_float4(v[4], v[5], 0.f, 0.f);
-        }
-    }
+// table, boxes and bucket boxes from the sorted order (shared tail of the single-GPU and the distributed build)
+template <bool GATHER>
+static int sor_finish(const float* xyz, int64_t n, const float* bmin, float cell, SorWs& w, cudaStream_t st) {
+    const uint64_t M64 = 0xFFFFFFFFFFFFFFFFull / (uint64_t)n;
+    GSX_CUDA_CHECK(cudaMemsetAsync(w.tab_se, 0, (size_t)n * sizeof(int2), st));
+    k_sor_finish<GATHER><<<(int)((n + 1023) / 1024), 1024, 0, st>>>(xyz, w.order, w.keys_sorted, w.spos, n, bmin[0],
+                                                                    bmin[1], bmin[2], cell, M64, w.tab_se, w.startbits,
+                                                                    w.caabb, w.saabb);
+    GSX_KERNEL_CHECK();
+    k_sor_bucket_boxes<<<(int)((n + 255) / 256), 256, 0, st>>>(w.startbits, w.spos, w.caabb, w.tab_se, n, bmin[0],
+                                                               bmin[1], bmin[2], cell, M64, w.tab_box);
+    GSX_KERNEL_CHECK();
+    return GSX_OK;
 }
 
 int sor_build(const float* xyz, int64_t n, const float* bmin, float cell, SorWs& w, cudaStream_t st) {
@@ -337,14 +389,7 @@ int sor_build(const float* xyz, int64_t n, const float* bmin, float cell, SorWs&
                                   w.sort_ws_bytes, &w.keys_sorted, &w.order, st);
         if (rc) return rc;
     }
-    GSX_CUDA_CHECK(cudaMemsetAsync(w.table, 0, (size_t)n * 2 * sizeof(float4), st));
-    k_sor_table<<<blocks, 256, 0, st>>>(w.keys_sorted, n, w.table);
-    GSX_KERNEL_CHECK();
-    k_sor_gather<<<(int)((n + 1023) / 1024), 1024, 0, st>>>(xyz, w.order, n, w.spos, w.caabb, w.saabb);
-    GSX_KERNEL_CHECK();
-    k_sor_bucket_boxes<<<blocks, 256, 0, st>>>(w.keys_sorted, w.spos, w.caabb, n, w.table);
-    GSX_KERNEL_CHECK();
-    return GSX_OK;
+    return sor_finish<true>(xyz, n, bmin, cell, w, st);
 }
 
 // ------------------------------------------------------------------ distributed build (one process per GPU)
@@ -352,32 +397,6 @@ int sor_build(const float* xyz, int64_t n, const float* bmin, float cell, SorWs&
 // slab by the GLOBAL bucket key, the runs are exchanged by owner (all-to-all, host side: gsx/dist.py), each
 // owner sorts what it received, the sorted float4 segments are all-gathered, and every rank fills its table,
 // boxes and bucket boxes from the (now identical) sorted array.  The sort work per rank drops from N to 2N/G.
-
-// hash (mod n) and in-cell Morton code of a point: shared by all key kernels
-__device__ __forceinline__ uint64_t bucket_key(float x, float y, float z, float bx, float by, float bz, float cell,
-                                               int64_t n, uint64_t M64) {
-    float fx = __fdiv_rn(__fsub_rn(x, bx), cell);
-    float fy = __fdiv_rn(__fsub_rn(y, by), cell);
-    float fz = __fdiv_rn(__fsub_rn(z, bz), cell);
-    float flx = floorf(fx), fly = floorf(fy), flz = floorf(fz);
-    int64_t gx = (int64_t)(int32_t)flx, gy = (int64_t)(int32_t)fly, gz = (int64_t)(int32_t)flz;
-    int64_t hx = (gx * 73856093LL) ^ (gy * 19349663LL) ^ (gz * 83492791LL);
-    int64_t h;
-    if (hx >= 0) {
-        uint64_t q = __umul64hi((uint64_t)hx, M64);
-        uint64_t r = (uint64_t)hx - q * (uint64_t)n;
-        while (r >= (uint64_t)n) r -= (uint64_t)n;
-        h = (int64_t)r;
-    } else {
-        h = hx % n;
-        if (h < 0) h += n;
-    }
-    uint32_t sx = (uint32_t)fminf(kMortonMax, fmaxf(0.f, (fx - flx) * kMortonScale));
-    uint32_t sy = (uint32_t)fminf(kMortonMax, fmaxf(0.f, (fy - fly) * kMortonScale));
-    uint32_t sz = (uint32_t)fminf(kMortonMax, fmaxf(0.f, (fz - flz) * kMortonScale));
-    uint32_t mort = (spread6(sx) << 2) | (spread6(sy) << 1) | spread6(sz);
-    return ((uint64_t)h << kMortonBits) | (uint64_t)mort;
-}
 
 // stage A: owner rank of every slab point (owner o holds the buckets [ceil(o*N/G), ceil((o+1)*N/G)))
 __global__ void __launch_bounds__(256) k_sor_owner_keys(const float* __restrict__ xyz, int64_t n, int64_t n_global,
@@ -481,82 +500,12 @@ int sor_dist_merge(const float4* pos4_in, int64_t m, int64_t n_global, const flo
 }
 
 // stage C: everything gsx_sor_build produces, from an already hash-sorted float4 array
-__global__ void __launch_bounds__(256) k_sor_keys_sorted(const float4* __restrict__ spos, int64_t n, float bx, float by,
-                                                         float bz, float cell, uint64_t M64,
-                                                         uint64_t* __restrict__ keys) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float4 p = spos[i];
-    uint64_t h = bucket_key(p.x, p.y, p.z, bx, by, bz, cell, n, M64) >> kMortonBits;
-    keys[i] = (uint64_t)h << kMortonBits;
-}
-
-// chunk / super boxes of an already sorted array (the box part of k_sor_gather)
-__global__ void __launch_bounds__(1024) k_sor_boxes_sorted(const float4* __restrict__ spos, int64_t n,
-                                                           float4* __restrict__ caabb, float4* __restrict__ saabb) {
-    int64_t j = (int64_t)blockIdx.x * 1024 + threadIdx.x;
-    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    if (j < n) {
-        float4 p = spos[j];
-        lo[0] = hi[0] = p.x;
-        lo[1] = hi[1] = p.y;
-        lo[2] = hi[2] = p.z;
-    }
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo[a] = fminf(lo[a], __shfl_xor_sync(GSX_FULL, lo[a], o));
-            hi[a] = fmaxf(hi[a], __shfl_xor_sync(GSX_FULL, hi[a], o));
-        }
-    __shared__ float sm[6][32];
-    int w = threadIdx.x >> 5;
-    int64_t chunk = (int64_t)blockIdx.x * 32 + w;
-    if (lane_id() == 0) {
-        if (chunk * 32 < n) {
-            caabb[2 * chunk] = make_float4(lo[0], lo[1], lo[2], hi[0]);
-            caabb[2 * chunk + 1] = make_float4(hi[1], hi[2], 0.f, 0.f);
-        }
-        for (int a = 0; a < 3; ++a) {
-            sm[a][w] = lo[a];
-            sm[3 + a][w] = hi[a];
-        }
-    }
-    __syncthreads();
-    if (w == 0) {
-        float v[6];
-#pragma unroll
-        for (int a = 0; a < 6; ++a) {
-            v[a] = sm[a][lane_id()];
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                float t = __shfl_xor_sync(GSX_FULL, v[a], o);
-                v[a] = a < 3 ? fminf(v[a], t) : fmaxf(v[a], t);
-            }
-        }
-        if (lane_id() == 0) {
-            saabb[2 * (int64_t)blockIdx.x] = make_float4(v[0], v[1], v[2], v[3]);
-            saabb[2 * (int64_t)blockIdx.x + 1] = make_float4(v[4], v[5], 0.f, 0.f);
-        }
-    }
-}
-
 int sor_build_from_sorted(const float4* spos_in, int64_t n, const float* bmin, float cell, SorWs& w, cudaStream_t st) {
-    int blocks = (int)((n + 255) / 256);
     if (spos_in != w.spos)
         GSX_CUDA_CHECK(cudaMemcpyAsync(w.spos, spos_in, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, st));
-    k_sor_keys_sorted<<<blocks, 256, 0, st>>>(w.spos, n, bmin[0], bmin[1], bmin[2], cell,
-                                              0xFFFFFFFFFFFFFFFFull / (uint64_t)n, w.keys0);
-    GSX_KERNEL_CHECK();
-    w.keys_sorted = w.keys0;
-    GSX_CUDA_CHECK(cudaMemsetAsync(w.table, 0, (size_t)n * 2 * sizeof(float4), st));
-    k_sor_table<<<blocks, 256, 0, st>>>(w.keys_sorted, n, w.table);
-    GSX_KERNEL_CHECK();
-    k_sor_boxes_sorted<<<(int)((n + 1023) / 1024), 1024, 0, st>>>(w.spos, n, w.caabb, w.saabb);
-    GSX_KERNEL_CHECK();
-    k_sor_bucket_boxes<<<blocks, 256, 0, st>>>(w.keys_sorted, w.spos, w.caabb, n, w.table);
-    GSX_KERNEL_CHECK();
-    return GSX_OK;
+    w.keys_sorted = nullptr;
+    w.order = nullptr;
+    return sor_finish<false>(nullptr, n, bmin, cell, w, st);
 }
 
 // ------------------------------------------------------------------ query kernel
@@ -680,7 +629,8 @@ __device__ __forceinline__ void scan32(const float4* __restrict__ spos, int64_t 
 #endif
 template <int NREG, bool STATS>
 __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
-    k_sor_knn(const float4* __restrict__ spos, const float4* __restrict__ table, const float4* __restrict__ caabb,
+    k_sor_knn(const float4* __restrict__ spos, const int2* __restrict__ tab_se, const float4* __restrict__ tab_box,
+              const float4* __restrict__ caabb,
               const float4* __restrict__ saabb, float* __restrict__ final_means, unsigned int* __restrict__ work,
               int64_t q_begin, int64_t q_end, int K, int hash_mode, float bx, float by, float bz, float cell,
               uint32_t n, uint64_t M, unsigned long long* __restrict__ stats) {
@@ -716,10 +666,13 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
                 ps = 0, pc = 0;
                 if (lane < 27) {
                     uint32_t h = probe_hash(gx + pdx, gy + pdy, gz + pdz, n, M, hash_mode);
-                    const float4 t0 = __ldg(table + 2 * (size_t)h), t1 = __ldg(table + 2 * (size_t)h + 1);
-                    ps = __float_as_int(t0.x);
-                    pc = __float_as_int(t0.y) - ps;
-                    blx = t0.z, bly = t0.w, blz = t1.x, bhx = t1.y, bhy = t1.z, bhz = t1.w;
+                    const int2 se = __ldg(tab_se + h);
+                    ps = se.x;
+                    pc = se.y - se.x;
+                    if (pc > 0) {  // the box of an empty bucket is never written (and never read)
+                        const float4 b0 = __ldg(tab_box + 2 * (size_t)h), b1 = __ldg(tab_box + 2 * (size_t)h + 1);
+                        blx = b0.x, bly = b0.y, blz = b0.z, bhx = b1.x, bhy = b1.y, bhz = b1.z;
+                    }
                 }
             }
             if (STATS) {
@@ -842,7 +795,7 @@ static int launch_knn(SorWs& w, int64_t q_begin, int64_t q_end, int K, int hash_
     int64_t grid = (int64_t)sm_count() * (per_sm > 0 ? per_sm : 4);  // persistent: exactly the resident CTAs
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
-    k_sor_knn<NREG, STATS><<<(int)grid, 256, 0, st>>>(w.spos, w.table, w.caabb, w.saabb, final_means, w.counters,
+    k_sor_knn<NREG, STATS><<<(int)grid, 256, 0, st>>>(w.spos, w.tab_se, w.tab_box, w.caabb, w.saabb, final_means, w.counters,
                                                       q_begin, q_end, K, hash_mode, bmin[0], bmin[1], bmin[2], cell,
                                                       (uint32_t)w.n, M, stats);
     return GSX_OK;

@@ -12,7 +12,9 @@ struct SorWs {
     uint64_t *keys0, *keys1, *keys_sorted;
     int32_t *vals0, *vals1, *order;
     float4* spos;   // hash-sorted positions, w = original index
-    float4* table;  // 2 float4 per bucket: {start, end (int bits), lo.x, lo.y}, {lo.z, hi.x, hi.y, hi.z}; {0,0,..} = empty
+    int2* tab_se;         // per bucket {start, end} in sorted order; {0,0} = empty (cell_start == -1)
+    float4* tab_box;      // per bucket {lo.xyz,-},{hi.xyz,-}: exact box of its points (occupied buckets only)
+    uint32_t* startbits;  // one bit per sorted position: starts a bucket
     float4* caabb;  // 2 float4 per 32-point chunk: {lo.x,lo.y,lo.z,hi.x},{hi.y,hi.z,-,-}
     float4* saabb;  // same per 1024-point super
     float* partial;

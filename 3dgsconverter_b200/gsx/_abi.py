@@ -71,11 +71,11 @@ _SIGS = {
     "gsx_lexsort_zyx": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp]),
     "gsx_quantize_to_codebook": (C.c_int, [_vp, _i64, _f32p, _i32, _vp, _vp, _i64, _vp]),
     "gsx_kmeans_workspace_bytes": (_i64, [_i64, _i32, _i32, _i32]),
-    "gsx_kmeans_set_prefilter": (None, [_i32]),
-    "gsx_kmeans_get_prefilter": (_i32, []),
     "gsx_kmeans_lloyd_device": (C.c_int, [_vp, C.POINTER(_i64), _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i64,
-                                          _vp]),
-    "gsx_kmeans_host": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp]),
+                                          _i32, _vp, _vp]),
+    "gsx_kmeans_tensor_core_supported": (_i32, [_i32, _i32]),
+    "gsx_kmeans_tc_debug_scores": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
+    "gsx_kmeans_host": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _i32]),
 }
 
 for _name, (_res, _args) in _SIGS.items():
@@ -84,6 +84,7 @@ for _name, (_res, _args) in _SIGS.items():
     _fn.argtypes = _args
 
 HASH_MODES = {"i32wrap": 0, "i64": 1}
+KM_ASSIGN = {"auto": 0, "strict": 1, "fma": 2, "tensor": 3}
 
 
 def check(rc: int, what: str = ""):

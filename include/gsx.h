@@ -38,8 +38,7 @@ extern "C" {
 const char* gsx_last_error(void);
 int gsx_version(void);          /* 100*major + minor */
 int gsx_device_sm_count(void);  /* SMs of the current device (grid sizing), <0 on error */
-long long gsx_kernel_launches(void); /* cumulative number of gsx kernels launched by this process (CUB's sort
-                                        kernels inside gsx_sor_build are not counted) */
+long long gsx_kernel_launches(void); /* cumulative number of gsx kernels launched by this process */
 
 /* ---- SOR, Taichi semantics: gpu_ops.py:193-263 (filter_sor_gpu) + :98-176 (kernel) - */
 
@@ -189,18 +188,31 @@ int gsx_quantize_to_codebook(const float* vals_dev, int64_t n, const float* code
  * One call = max_iter x (assign ; update) with the serial index-order float32 sums of SURVEY A.5.
  * labels are those of the last assign (one update behind C); counts int32[nprob*K]. */
 int64_t gsx_kmeans_workspace_bytes(int64_t n_total, int32_t nprob, int32_t K, int32_t D);
-/* Exact pre-filter of the assign step (D >= 9): one fma per (point, centroid, dim) scores every centroid, the strict
- * contract distance is evaluated only for the centroids within a proven rounding-error margin of the best score.
- * Labels are bit-identical either way; process-wide switch, default off. */
-void gsx_kmeans_set_prefilter(int32_t on);
-int32_t gsx_kmeans_get_prefilter(void);
+/* assign_mode (per call; the labels are bit-identical in every mode):
+ *   AUTO           tensor cores when the shape allows it (gsx_kmeans_tensor_core_supported), else STRICT
+ *   STRICT         the contract's distance for every (point, centroid) on the FP32 pipes
+ *   FMA_PREFILTER  D >= 9: one fma per (point, centroid, dim) scores every centroid, the strict distance is
+ *                  evaluated only for the centroids within a proven rounding-error margin of the best score
+ *   TENSOR         the same scheme with the score matrix X.C^T - ||c||^2/2 computed by tcgen05.mma (TF32 inputs,
+ *                  float32 accumulators in TMEM); error if the shape is unsupported (D in {9,24,45}, K <= 256)
+ * tc_stats_dev (may be NULL): 3 uint64 counters accumulated by the TENSOR path {strict distance evaluations,
+ * points with more than one candidate, points that needed the full strict scan}. */
+#define GSX_KM_ASSIGN_AUTO 0
+#define GSX_KM_ASSIGN_STRICT 1
+#define GSX_KM_ASSIGN_FMA_PREFILTER 2
+#define GSX_KM_ASSIGN_TENSOR 3
 int gsx_kmeans_lloyd_device(const float* X_dev, const int64_t* row_off_host, int32_t nprob, int32_t K, int32_t D,
                             int32_t max_iter, float* C_dev, int32_t* labels_dev, int32_t* counts_dev, void* ws,
-                            int64_t ws_bytes, void* stream);
+                            int64_t ws_bytes, int32_t assign_mode, unsigned long long* tc_stats_dev, void* stream);
+int32_t gsx_kmeans_tensor_core_supported(int32_t K, int32_t D);
+/* Test hook of the tensor-core assign: raw scores s[r][c] = x_r.c - ||c||^2/2 of the first min(rows,128) rows
+ * against the K centroids, scores_dev float32[128 * roundup32(K)].  ws >= 1024 bytes. */
+int gsx_kmeans_tc_debug_scores(const float* X_dev, int64_t rows, const float* C_dev, int32_t K, int32_t D,
+                               int32_t variant, float* scores_dev, void* ws, int64_t ws_bytes, void* stream);
 /* Single problem on HOST buffers: binding target for gpu_ops.kmeans on the GPU path (gpu_ops.py:178-191)
  * with the init centroids chosen by the caller (the reference's np.random.choice draw). */
 int gsx_kmeans_host(const float* X_host, int64_t n, int32_t K, int32_t D, int32_t max_iter, float* C_host_inout,
-                    int32_t* labels_host);
+                    int32_t* labels_host, int32_t assign_mode);
 
 #ifdef __cplusplus
 }
