@@ -209,6 +209,20 @@ int gsx_mean_std_f32(const float* a_dev, int64_t n, float* out_dev, void* ws, in
     return mean_std_f32(a_dev, n, out_dev, ws, (size_t)ws_bytes, (cudaStream_t)stream);
 }
 
+int64_t gsx_pairwise_slots(int64_t n) { return pairwise_slots(n); }
+
+int gsx_pairwise_leaves_dist(const float* a_local_dev, int64_t base, int64_t n_local, int64_t n_global, int32_t sq,
+                             const float* meanstd_dev, const float* halo_dev, const int64_t* bases_dev, int32_t world,
+                             float* slot_dev, void* stream) {
+    return pairwise_leaves_dist(a_local_dev, base, n_local, n_global, sq, meanstd_dev, halo_dev,
+                                (const long long*)bases_dev, world, slot_dev, (cudaStream_t)stream);
+}
+
+int gsx_pairwise_finish(float* slot_dev, int64_t n_global, int32_t sq, float* meanstd_dev, void* stream) {
+    GSX_REQUIRE(n_global >= 1, GSX_ERR_ARG, "pairwise_finish: n must be >= 1");
+    return pairwise_finish(slot_dev, n_global, sq, meanstd_dev, (cudaStream_t)stream);
+}
+
 int gsx_threshold_mask(const float* a_dev, int64_t n, const float* meanstd_dev, float threshold_factor,
                        uint8_t* mask_dev, void* stream) {
     return threshold_mask(a_dev, n, meanstd_dev, threshold_factor, mask_dev, (cudaStream_t)stream);

@@ -528,8 +528,11 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// phase 5: one warp per (problem, cluster): serial index-order float32 sums over the member list
-__global__ void __launch_bounds__(256)
+// phase 5: one warp per (problem, cluster): serial index-order float32 sums over the member list.
+// The chain of adds is inherently sequential (float32 addition does not associate), but it is short (~3 000 adds);
+// what limits the warp is the latency of gathering its ~3 000 rows.  So a whole batch of 32 member rows is put in
+// flight at once (64 independent loads per lane) before the 32 dependent adds are issued, in index order.
+__global__ void __launch_bounds__(128)
     k_km_accum(const float* __restrict__ X, float* __restrict__ C, const int* __restrict__ member,
                const int* __restrict__ offs, const int* __restrict__ counts, const KmProb* __restrict__ probs,
                int nprob, int K, int D) {
@@ -546,30 +549,31 @@ __global__ void __launch_bounds__(256)
     for (int d0 = 0; d0 < D; d0 += 64) {
         const int da = d0 + lane, db = d0 + 32 + lane;
         const bool ha = da < D, hb = db < D;
+        const int oa = ha ? da : 0, ob = hb ? db : 0;  // clamped: every load is in bounds, unused lanes add nothing
         float sa = 0.f, sb = 0.f;
-        for (int base = 0; base < cnt; base += 32) {
-            const int mine = base + lane < cnt ? __ldg(mem + base + lane) : 0;
-            const int nn = cnt - base < 32 ? cnt - base : 32;
-            int u = 0;
-            for (; u + 8 <= nn; u += 8) {  // 8 rows in flight, then 8 adds in index order
-                float va[8], vb[8];
+        int base = 0;
+        int mine = lane < cnt ? __ldg(mem + lane) : 0;
+        for (; base + 32 <= cnt; base += 32) {
+            const int nxt = base + 32 + lane < cnt ? __ldg(mem + base + 32 + lane) : 0;  // next batch's indices
+            float va[32], vb[32];
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    const float* xr = Xp + (size_t)__shfl_sync(GSX_FULL, mine, u + t) * D;
-                    va[t] = ha ? __ldg(xr + da) : 0.f;
-                    vb[t] = hb ? __ldg(xr + db) : 0.f;
-                }
+            for (int t = 0; t < 32; ++t) {
+                const float* xr = Xp + (size_t)__shfl_sync(GSX_FULL, mine, t) * D;
+                va[t] = __ldg(xr + oa);
+                vb[t] = __ldg(xr + ob);
+            }
 #pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    sa = __fadd_rn(sa, va[t]);
-                    sb = __fadd_rn(sb, vb[t]);
-                }
+            for (int t = 0; t < 32; ++t) {
+                sa = __fadd_rn(sa, va[t]);
+                sb = __fadd_rn(sb, vb[t]);
             }
-            for (; u < nn; ++u) {
-                const float* xr = Xp + (size_t)__shfl_sync(GSX_FULL, mine, u) * D;
-                if (ha) sa = __fadd_rn(sa, __ldg(xr + da));
-                if (hb) sb = __fadd_rn(sb, __ldg(xr + db));
-            }
+            mine = nxt;
+        }
+        const int nn = cnt - base;  // ragged tail (< 32 rows)
+        for (int u = 0; u < nn; ++u) {
+            const float* xr = Xp + (size_t)__shfl_sync(GSX_FULL, mine, u) * D;
+            sa = __fadd_rn(sa, __ldg(xr + oa));
+            sb = __fadd_rn(sb, __ldg(xr + ob));
         }
         if (cnt > 0) {
             sa = __fmul_rn(sa, inv);
@@ -690,6 +694,7 @@ int kmeans_lloyd(const float* X, const int64_t* row_off, int nprob, int K, int D
     GSX_CUDA_CHECK(cudaStreamSynchronize(st));  // hp is a local pageable buffer
     const long long uwarps = (long long)nprob * K;
     const int ublocks = (int)((uwarps * 32 + 255) / 256);
+    const int ablocks = (int)((uwarps * 32 + 127) / 128);
     const bool sorted = K <= kMaxSortK;
     const size_t smem = (size_t)8 * (K + 1) * sizeof(int);
     if (sorted && smem > 48 * 1024) {
@@ -729,7 +734,7 @@ int kmeans_lloyd(const float* X, const int64_t* row_off, int nprob, int K, int D
         GSX_KERNEL_CHECK();
         k_km_scatter<<<sblocks, 256, smem, st>>>(labels, dp, nprob, K, (int)nsub, w.hist, w.offs, w.member);
         GSX_KERNEL_CHECK();
-        k_km_accum<<<ublocks, 256, 0, st>>>(X, C, w.member, w.offs, counts, dp, nprob, K, D);
+        k_km_accum<<<ablocks, 128, 0, st>>>(X, C, w.member, w.offs, counts, dp, nprob, K, D);
         GSX_KERNEL_CHECK();
     }
     if (use_tc && max_iter > 0) {  // a timed-out mbarrier wait inside the tensor-core kernel (protocol bug) is an error

@@ -31,7 +31,7 @@ namespace gsx {
 
 #define GSX_FULL 0xffffffffu
 
-constexpr int kTcThreads = 128;   // one thread per point row == one TMEM lane
+constexpr int kTcThreads = 256;   // two threads per point row (TMEM lane): they split the centroid columns
 constexpr int kTcRows = 128;      // UMMA M
 constexpr int kTcMaxN = 256;      // UMMA N limit == max centroids of the tensor-core path
 constexpr unsigned kSpinLimit = 1u << 26;  // bounded mbarrier waits: a protocol bug must not hang the GPU
@@ -130,18 +130,32 @@ struct TcShared {  // tail of the dynamic shared memory (after the operand tiles
     uint64_t bar_copy;
     uint64_t bar_mma;
     uint32_t tmem_base;
-    float cmax;
-    float red[4];
+    float red[8];
+    float xn[2][kTcRows];    // partial ||x||^2 of the two half rows
+    float pmax[2][kTcRows];  // partial row maxima of the two column halves
+    int pcnt[2][kTcRows];    // candidates in each column half
+    float pbest[kTcRows];    // strict result of the upper column half
+    int pbk[kTcRows];
 };
 
+// barrier of the two warps that share a TMEM lane quarter (warp q and warp q+4): ids 1..4, 64 threads
+__device__ __forceinline__ void pair_sync(int q) { asm volatile("bar.sync %0, 64;" ::"r"(q + 1) : "memory"); }
+
+// Work split: 256 threads = 8 warps.  Warp w may only read the TMEM lanes 32*(w%4) .. +31, so warps q and q+4 share
+// the 32 point rows of lane quarter q and split the centroid COLUMNS between them (lower / upper half of the 32-wide
+// column chunks); the pair exchanges its partial row maximum, candidate count and strict result through shared
+// memory behind a 64-thread named barrier.  Two CTAs per SM (2 x 256 TMEM columns) = 16 resident warps.
 // mode 0: labels; mode 1 (debug): dump the raw scores of the first tile to dump[128*npad] and return
 template <int D, int KP>
-__global__ void __launch_bounds__(kTcThreads)
+__global__ void __launch_bounds__(kTcThreads, 2)
     k_km_assign_tc(const float* __restrict__ X, long long x_floats, const float* __restrict__ C,
                    int* __restrict__ labels, const KmProb* __restrict__ probs, int nprob, int K, int npad,
                    int tmem_cols, long long tiles_total, int desc_variant, int mode, float* __restrict__ dump,
                    unsigned long long* __restrict__ tc_stats, int* __restrict__ err_flag) {
     static_assert(KP % 8 == 0 && KP >= D + 3, "K padding");
+    constexpr int G4 = KP / 4;              // float4 groups per operand row
+    constexpr int GH = (G4 + 1) / 2;        // groups re-laid by the lower-half thread of a row
+    constexpr int NCH = kTcMaxN / 32;       // 32-column chunks of the accumulator (8)
     extern __shared__ __align__(1024) unsigned char smem[];
     unsigned char* sB = smem;                                   // [kTcMaxN x KP] float32, UMMA K-major layout
     unsigned char* sA = sB + kTcMaxN * KP * 4;                  // [128 x KP]
@@ -149,6 +163,8 @@ __global__ void __launch_bounds__(kTcThreads)
     TcShared* sh = reinterpret_cast<TcShared*>(reinterpret_cast<unsigned char*>(sStage) + (kTcRows * D + 8) * 4);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int q = warp & 3, half = warp >> 2;
+    const int row = q * 32 + lane;  // point row of the tile == TMEM lane
     if (tid == 0) {
         mbar_init(&sh->bar_copy, 1);
         mbar_init(&sh->bar_mma, 1);
@@ -163,15 +179,18 @@ __global__ void __launch_bounds__(kTcThreads)
     const long long t0 = tiles_total * (long long)blockIdx.x / gridDim.x;
     const long long t1 = tiles_total * (long long)(blockIdx.x + 1) / gridDim.x;
     const bool x_aligned = (reinterpret_cast<uintptr_t>(X) & 15) == 0;
-    const uint32_t lbo = desc_variant == 1 ? (uint32_t)(KP / 4) * 128u : 128u;
-    const uint32_t sbo = desc_variant == 1 ? 128u : (uint32_t)(KP / 4) * 128u;
+    const uint32_t lbo = desc_variant == 1 ? (uint32_t)G4 * 128u : 128u;
+    const uint32_t sbo = desc_variant == 1 ? 128u : (uint32_t)G4 * 128u;
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(npad >> 3) << 17) | ((kTcRows >> 4) << 24);
     constexpr float kU = 5.9604645e-8f;                        // 2^-24
     constexpr float kGs = 2.f * (D + 3) * kU * 1.02f;          // >= 2 gamma_{D+2} / (1 - gamma_{D+2})
     constexpr float kEpsIn = 1.953125e-3f * 1.01f;             // 2^-9 (+): two TF32 conversions, 2^-10 each
     constexpr float kEpsAcc = 3.0517578e-5f;                   // 2^-15: accumulation + bias evaluation slack
+    // this thread's column chunks: the lower half of the chunks for warps 0-3, the upper half for warps 4-7
+    const int nch = npad >> 5;
+    const int ch_lo = half == 0 ? 0 : (nch + 1) / 2;
+    const int ch_hi = half == 0 ? (nch + 1) / 2 : nch;
 
-    // geometry of tile t: problem, first row, rows, and whether the bulk copy may be used
     struct TileGeo { int p; long long row0; int rows; long long off_floats; bool bulk; uint32_t pre, bytes; };
     auto geo = [&](long long t) {
         TileGeo g;
@@ -212,8 +231,8 @@ __global__ void __launch_bounds__(kTcThreads)
         const float* Cp = C + (size_t)g.p * K * D;
         if (g.p != cur_prob) {  // (re)load the centroids of this problem as the B operand
             __syncthreads();    // nobody is still reading sB in a strict evaluation of the previous tile
-            for (int idx = tid; idx < npad * (KP / 4); idx += kTcThreads) {
-                const int c = idx / (KP / 4), j = idx - c * (KP / 4);
+            for (int idx = tid; idx < npad * G4; idx += kTcThreads) {
+                const int c = idx / G4, j = idx - c * G4;
                 float v[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -236,7 +255,7 @@ __global__ void __launch_bounds__(kTcThreads)
                 // bias = -0.5||c||^2 as three TF32-exact pieces; padding centroids get a huge negative score
                 const float b = c < K ? -0.5f * cn : -3.0e38f;
                 const float bh = tf32_trunc(b);
-                const float r1 = c < K ? b - bh : 0.f;       // exact (Sterbenz-like: same exponent range)
+                const float r1 = c < K ? b - bh : 0.f;       // exact: the low 13 bits
                 const float bm = tf32_trunc(r1);
                 const float bl = c < K ? r1 - bm : 0.f;      // <= 2 significant bits left: TF32-exact
                 *reinterpret_cast<float*>(sB + op_off<KP>(c, D)) = bh;
@@ -247,35 +266,42 @@ __global__ void __launch_bounds__(kTcThreads)
             for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(GSX_FULL, mx, o));
             if (lane == 0) sh->red[warp] = mx;
             __syncthreads();
-            mx = fmaxf(fmaxf(sh->red[0], sh->red[1]), fmaxf(sh->red[2], sh->red[3]));
+            mx = sh->red[0];
+#pragma unroll
+            for (int w = 1; w < kTcThreads / 32; ++w) mx = fmaxf(mx, sh->red[w]);
             Cm = sqrtf(mx) * 1.0001f;  // inf/NaN propagate into the margin -> full strict scan below
             cur_prob = g.p;
         }
 
-        // ---- this thread's row: staging (bulk copy) or global -> UMMA layout, ||x||^2 on the way
+        // ---- this thread's half row: staging (bulk copy) or global -> UMMA layout, partial ||x||^2 on the way
         if (g.bulk) {
             if (!mbar_wait(&sh->bar_copy, copy_phase)) failed = true;
             copy_phase ^= 1;
         }
-        const bool live = tid < g.rows;
-        float xn = 0.f;
+        const bool live = row < g.rows;
         {
-            const float* src = g.bulk ? sStage + (g.pre >> 2) + tid * D : X + g.off_floats + (long long)tid * D;
+            const float* src = g.bulk ? sStage + (g.pre >> 2) + row * D : X + g.off_floats + (long long)row * D;
+            float xa = 0.f, xb = 0.f;  // two chains
+            const int j0 = half == 0 ? 0 : GH, j1 = half == 0 ? GH : G4;
 #pragma unroll
-            for (int j = 0; j < KP / 4; ++j) {
-                float v[4];
+            for (int jj = 0; jj < GH; ++jj) {
+                const int j = j0 + jj;
+                if (j < j1) {
+                    float v[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int k = 4 * j + e;
-                    if (k < D) {
-                        v[e] = live ? src[k] : 0.f;
-                        xn = __fmaf_rn(v[e], v[e], xn);
-                    } else {
-                        v[e] = k < D + 3 ? 1.0f : 0.f;
+                    for (int e = 0; e < 4; ++e) {
+                        const int k = 4 * j + e;
+                        if (k < D) {
+                            v[e] = live ? src[k] : 0.f;
+                            if (e & 1) xb = __fmaf_rn(v[e], v[e], xb); else xa = __fmaf_rn(v[e], v[e], xa);
+                        } else {
+                            v[e] = k < D + 3 ? 1.0f : 0.f;
+                        }
                     }
+                    *reinterpret_cast<float4*>(sA + op_off<KP>(row, 4 * j)) = make_float4(v[0], v[1], v[2], v[3]);
                 }
-                *reinterpret_cast<float4*>(sA + op_off<KP>(tid, 4 * j)) = make_float4(v[0], v[1], v[2], v[3]);
             }
+            sh->xn[half][row] = xa + xb;
         }
         fence_proxy_async();   // generic-proxy writes of sA / sB -> visible to the tensor core (async proxy)
         tc_fence_before();     // this thread's tcgen05.ld of the previous tile are done before the next MMA
@@ -283,7 +309,7 @@ __global__ void __launch_bounds__(kTcThreads)
         if (t + 1 < t1) cur = geo(t + 1);
         if (tid == 0) {
             tc_fence_after();
-            if (t + 1 < t1 && cur.bulk) {  // staging is free: every thread has copied its row out
+            if (t + 1 < t1 && cur.bulk) {  // staging is free: every thread has copied its half row out
                 mbar_expect_tx(&sh->bar_copy, cur.bytes);
                 bulk_g2s(sStage, reinterpret_cast<const char*>(X) + (cur.off_floats * 4 - cur.pre), cur.bytes,
                          &sh->bar_copy);
@@ -301,71 +327,89 @@ __global__ void __launch_bounds__(kTcThreads)
         tc_fence_after();
         if (failed) break;
 
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
         if (mode == 1) {  // debug: raw scores of the tile
-            for (int c0 = 0; c0 < npad; c0 += 32) {
+            for (int w = ch_lo; w < ch_hi; ++w) {
                 float v[32];
-                tmem_ld32(taddr + c0, v);
+                tmem_ld32(taddr + w * 32, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) dump[(size_t)tid * npad + c0 + i] = v[i];
+                for (int i = 0; i < 32; ++i) dump[(size_t)row * npad + w * 32 + i] = v[i];
             }
             break;
         }
 
-        // ---- epilogue: row maximum, candidate mask, strict evaluation of the candidates
-        float smax = -INFINITY;
+        // ---- epilogue pass 1: row maximum over this thread's column chunks (four independent chains)
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-        for (int w = 0; w < kTcMaxN / 32; ++w) {
-            if (w * 32 < npad) {
+        for (int ww = 0; ww < NCH / 2; ++ww) {
+            const int w = ch_lo + ww;
+            if (w < ch_hi) {
                 float v[32];
                 tmem_ld32(taddr + w * 32, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) smax = fmaxf(smax, v[i]);
+                for (int i = 0; i < 32; i += 4) {
+                    m0 = fmaxf(m0, v[i]);
+                    m1 = fmaxf(m1, v[i + 1]);
+                    m2 = fmaxf(m2, v[i + 2]);
+                    m3 = fmaxf(m3, v[i + 3]);
+                }
             }
         }
+        sh->pmax[half][row] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        pair_sync(q);
+        const float smax = fmaxf(sh->pmax[0][row], sh->pmax[1][row]);
+        const float xn = sh->xn[0][row] + sh->xn[1][row];
         const float xnu = xn * 1.0001f;
         const float xnorm = sqrtf(xnu) * 1.0001f;
         const float eta = (kEpsIn * xnorm * Cm + kEpsAcc * (xnorm * Cm + Cm * Cm)) * 1.5f + 1e-37f;
         const float e_ub = fmaxf(xnu - 2.f * smax + 2.f * eta, 0.f);
         const float marg = 2.f * eta + kGs * e_ub;
         const float thr = smax - marg;
-        uint32_t mask[kTcMaxN / 32];
+        // ---- pass 2: candidate mask of this thread's chunks (two independent mask chains per chunk)
+        uint32_t mask[NCH / 2];
         int cnt = 0;
 #pragma unroll
-        for (int w = 0; w < kTcMaxN / 32; ++w) {
-            mask[w] = 0;
-            if (w * 32 < npad) {
+        for (int ww = 0; ww < NCH / 2; ++ww) {
+            mask[ww] = 0;
+            const int w = ch_lo + ww;
+            if (w < ch_hi) {
                 float v[32];
                 tmem_ld32(taddr + w * 32, v);
-                uint32_t m = 0;
+                uint32_t ma = 0, mb = 0;
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (v[i] >= thr) m |= 1u << i;
-                mask[w] = m;
-                cnt += __popc(m);
+                for (int i = 0; i < 32; i += 2) {
+                    if (v[i] >= thr) ma |= 1u << i;
+                    if (v[i + 1] >= thr) mb |= 1u << (i + 1);
+                }
+                mask[ww] = ma | mb;
+                cnt += __popc(ma | mb);
             }
         }
+        sh->pcnt[half][row] = cnt;
+        pair_sync(q);
+        const int total = sh->pcnt[0][row] + sh->pcnt[1][row];
         // the shortcut is only legal when the margin is finite, a real centroid scored, and the strict distance
-        // of the winner cannot reach the contract's 1e20 "no label" sentinel
-        const bool bad = !(marg < 3.0e38f) || !(smax > -1.0e30f) || !(e_ub < 1.0e19f) || cnt == 0;
-        int label = -1;
-        if (!bad && cnt == 1) {
+        // of the winner cannot reach the contract's 1e20 "no label" sentinel.  Both threads of a row agree on it.
+        const bool bad = !(marg < 3.0e38f) || !(smax > -1.0e30f) || !(e_ub < 1.0e19f) || total == 0;
+        if (!bad && total == 1 && cnt == 1 && live) {  // the single candidate lies in this thread's half
+            int label = -1;
 #pragma unroll
-            for (int w = 0; w < kTcMaxN / 32; ++w)
-                if (mask[w]) label = w * 32 + __ffs(mask[w]) - 1;
+            for (int ww = 0; ww < NCH / 2; ++ww)
+                if (mask[ww]) label = (ch_lo + ww) * 32 + __ffs(mask[ww]) - 1;
+            labels[g.row0 + row] = label;
         }
-        const bool need = live && (bad || cnt > 1);
-        if (__any_sync(GSX_FULL, need)) {
-            if (bad) {  // full strict scan over the real centroids
+        const bool need = live && (bad || total > 1);
+        if (__any_sync(GSX_FULL, need)) {  // same rows in both warps of the pair: both take this branch together
+            if (bad) {  // full strict scan over the real centroids of this half
 #pragma unroll
-                for (int w = 0; w < kTcMaxN / 32; ++w) {
-                    const int left = K - w * 32;
-                    mask[w] = left >= 32 ? 0xffffffffu : (left > 0 ? (1u << left) - 1u : 0u);
+                for (int ww = 0; ww < NCH / 2; ++ww) {
+                    const int left = K - (ch_lo + ww) * 32;
+                    mask[ww] = (ch_lo + ww < ch_hi) ? (left >= 32 ? 0xffffffffu : (left > 0 ? (1u << left) - 1u : 0u)) : 0u;
                 }
             }
             float best = 1e20f;
             int bk = -1;
-            if (need) {
+            if (need && half == 0) {
                 ++st_multi;
                 if (bad) ++st_full;
             }
@@ -373,18 +417,18 @@ __global__ void __launch_bounds__(kTcThreads)
                 int c = -1;
                 if (need) {
 #pragma unroll
-                    for (int w = kTcMaxN / 32 - 1; w >= 0; --w)
-                        if (mask[w]) c = w * 32 + __ffs(mask[w]) - 1;
+                    for (int ww = NCH / 2 - 1; ww >= 0; --ww)
+                        if (mask[ww]) c = (ch_lo + ww) * 32 + __ffs(mask[ww]) - 1;
                 }
                 if (!__any_sync(GSX_FULL, c >= 0)) break;
                 if (c >= 0) {
 #pragma unroll
-                    for (int w = 0; w < kTcMaxN / 32; ++w)
-                        if ((c >> 5) == w) mask[w] &= mask[w] - 1;
+                    for (int ww = 0; ww < NCH / 2; ++ww)
+                        if ((c >> 5) - ch_lo == ww) mask[ww] &= mask[ww] - 1;
                     float acc = 0.f;
 #pragma unroll
                     for (int j = 0; j < (D + 3) / 4; ++j) {
-                        const float4 xv = *reinterpret_cast<const float4*>(sA + op_off<KP>(tid, 4 * j));
+                        const float4 xv = *reinterpret_cast<const float4*>(sA + op_off<KP>(row, 4 * j));
                         const float4 cv = *reinterpret_cast<const float4*>(sB + op_off<KP>(c, 4 * j));
                         const float xa[4] = {xv.x, xv.y, xv.z, xv.w}, ca[4] = {cv.x, cv.y, cv.z, cv.w};
 #pragma unroll
@@ -398,9 +442,18 @@ __global__ void __launch_bounds__(kTcThreads)
                     if (acc < best) best = acc, bk = c;
                 }
             }
-            if (need) label = bk;
+            if (half == 1) {
+                sh->pbest[row] = best;
+                sh->pbk[row] = bk;
+            }
+            pair_sync(q);
+            if (half == 0 && need) {  // ascending index + strict '<': the lower half wins ties
+                const float hb = sh->pbest[row];
+                if (hb < best) bk = sh->pbk[row];
+                labels[g.row0 + row] = bk;
+            }
+            pair_sync(q);  // pbest / pbk are free again
         }
-        if (live) labels[g.row0 + tid] = label;
     }
 
     if (failed && err_flag) atomicExch(err_flag, 1);

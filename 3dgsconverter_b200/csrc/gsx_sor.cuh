@@ -47,6 +47,10 @@ int sor_build_from_sorted(const float4* spos_in, int64_t n, const float* bmin, f
 
 size_t mean_std_ws_bytes(int64_t n);
 int mean_std_f32(const float* a, int64_t n, float* out_dev, void* ws, size_t ws_bytes, cudaStream_t st);
+int64_t pairwise_slots(int64_t n);
+int pairwise_leaves_dist(const float* a_local, int64_t base, int64_t n_local, int64_t n, int sq, const float* meanstd,
+                         const float* halo, const long long* bases_dev, int world, float* slot, cudaStream_t st);
+int pairwise_finish(float* slot, int64_t n, int sq, float* meanstd, cudaStream_t st);
 int threshold_mask(const float* a, int64_t n, const float* meanstd_dev, float tf, uint8_t* mask, cudaStream_t st);
 
 }  // namespace gsx

@@ -162,6 +162,94 @@ int mean_std_f32(const float* a, int64_t n, float* out_dev, void* ws, size_t ws_
     return pairwise_pass<true>(a, n, dmax, slot, out_dev, st);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Sharded form (one process per GPU): the vector of n elements is cut into contiguous slabs, rank r holds
+// a[bases[r] .. bases[r+1]).  NumPy's tree depends only on n, so every leaf (<= 128 consecutive elements) is
+// summed by the rank whose slab contains the leaf's FIRST element; the (at most 127) elements of a leaf that
+// spill into the following slabs come from `halo` = the first 128 elements of every slab (all-gathered by the
+// caller).  Every slot is written by exactly one rank (0 elsewhere), so an all-reduce(sum) of the slot array is
+// exact; the inner nodes are then combined replicated (pairwise_finish).  Same bits as mean_std_f32 on the
+// concatenated vector.
+template <bool SQ>
+__global__ void __launch_bounds__(128)
+    k_pw_leaves_dist(const float* __restrict__ a_local, int64_t base, int64_t n_local, int64_t n, int dmax,
+                     const float* __restrict__ meanp, const float* __restrict__ halo,
+                     const long long* __restrict__ bases, int world, float* __restrict__ slot) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (1u << dmax)) return;
+    int64_t off, m;
+    int reached;
+    bool full = walk(n, dmax, t, off, m, reached);
+    if (!full && (t & ((1u << (dmax - reached)) - 1u))) return;
+    if (off < base || off >= base + n_local) return;  // another rank owns this leaf
+    const float mean = SQ ? meanp[0] : 0.f;
+    int hr = 0;  // slab that holds the spill-over elements (advances monotonically)
+    auto get = [&](int64_t i) -> float {
+        float v;
+        if (i < base + n_local) {
+            v = a_local[i - base];
+        } else {
+            while (hr + 1 < world && i >= bases[hr + 1]) ++hr;
+            v = halo[(size_t)hr * 128 + (i - bases[hr])];
+        }
+        if (SQ) {
+            float d = __fsub_rn(v, mean);
+            v = __fmul_rn(d, d);
+        }
+        return v;
+    };
+    float res;
+    if (m < 8) {
+        res = 0.f;
+        for (int64_t i = 0; i < m; ++i) res = __fadd_rn(res, get(off + i));
+    } else {
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = get(off + j);
+        int64_t i;
+        for (i = 8; i < m - (m % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], get(off + i + j));
+        }
+        res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+        for (; i < m; ++i) res = __fadd_rn(res, get(off + i));
+    }
+    slot[t] = res;
+}
+
+int64_t pairwise_slots(int64_t n) {
+    if (n < 1) n = 1;
+    return (int64_t)1 << pairwise_depth(n);
+}
+
+int pairwise_leaves_dist(const float* a_local, int64_t base, int64_t n_local, int64_t n, int sq, const float* meanstd,
+                         const float* halo, const long long* bases_dev, int world, float* slot, cudaStream_t st) {
+    GSX_REQUIRE(n >= 1 && n_local >= 0 && base >= 0 && base + n_local <= n, GSX_ERR_ARG, "pairwise_dist: bad slab");
+    int dmax = pairwise_depth(n);
+    GSX_REQUIRE(dmax <= 31, GSX_ERR_UNSUPPORTED, "pairwise_dist: n too large");
+    uint32_t leaves = 1u << dmax;
+    GSX_CUDA_CHECK(cudaMemsetAsync(slot, 0, (size_t)leaves * sizeof(float), st));
+    if (n_local == 0) return GSX_OK;
+    if (sq) k_pw_leaves_dist<true><<<(leaves + 127) / 128, 128, 0, st>>>(a_local, base, n_local, n, dmax, meanstd, halo, bases_dev, world, slot);
+    else k_pw_leaves_dist<false><<<(leaves + 127) / 128, 128, 0, st>>>(a_local, base, n_local, n, dmax, meanstd, halo, bases_dev, world, slot);
+    GSX_KERNEL_CHECK();
+    return GSX_OK;
+}
+
+int pairwise_finish(float* slot, int64_t n, int sq, float* meanstd, cudaStream_t st) {
+    int dmax = pairwise_depth(n);
+    int d = dmax - 1;
+    for (; d > 9; --d) {
+        k_pw_level<<<((1u << d) + 255) / 256, 256, 0, st>>>(n, dmax, d, slot);
+        GSX_KERNEL_CHECK();
+    }
+    if (sq) k_pw_top<true><<<1, 1024, 0, st>>>(n, dmax, d, slot, meanstd);
+    else k_pw_top<false><<<1, 1024, 0, st>>>(n, dmax, d, slot, meanstd);
+    GSX_KERNEL_CHECK();
+    return GSX_OK;
+}
+
 // gpu_ops.py:261-263: thresh = mean + f32(tf) * std (float32 mul then add), mask = a < thresh
 __global__ void __launch_bounds__(256) k_threshold_mask(const float* __restrict__ a, int64_t n,
                                                         const float* __restrict__ ms, float tf,

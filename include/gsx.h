@@ -65,8 +65,9 @@ int gsx_sor_build(const float* xyz_dev, int64_t n, const float* bmin_host, float
  *     -> the caller exchanges the groups (all-to-all).
  *  B. merge:      sorts the m received points of this rank's bucket range by (bucket, in-cell Morton)
  *     -> the caller all-gathers the segments in owner order = the globally hash-sorted array.
- *  C. build_from_sorted: table, bucket boxes and chunk/super boxes from that array (what gsx_sor_build
- *     leaves in the workspace), after which gsx_sor_mean_dists[_range] can run.  If spos4_dev already points at
+ *  C. build_from_sorted: bucket table ({start,end} per bucket, 8 B, the only part that is pre-zeroed), bucket boxes
+ *     and chunk/super boxes from that array in one fused pass + one pass over the bucket starts (what
+ *     gsx_sor_build leaves in the workspace), after which gsx_sor_mean_dists[_range] can run.  If spos4_dev already points at
  *     ws + gsx_sor_spos_offset(n) (all-gather straight into the workspace) no copy is made.
  * ws of A and B: gsx_sor_workspace_bytes(n_local) resp. (m); of C: gsx_sor_workspace_bytes(n_global). */
 int gsx_sor_dist_local_run(const float* xyz_local_dev, int64_t n_local, int64_t idx_base, int64_t n_global,
@@ -102,6 +103,19 @@ int gsx_sort_pairs(uint64_t* keys_dev, int32_t* vals_dev, int64_t n, int32_t beg
  * float32 accumulators and NumPy's pairwise summation order, bit-for-bit.  out_dev[0]=mean, [1]=std. */
 int64_t gsx_mean_std_workspace_bytes(int64_t n);
 int gsx_mean_std_f32(const float* a_dev, int64_t n, float* out_dev, void* ws, int64_t ws_bytes, void* stream);
+
+/* The same statistics for a vector sharded over G processes (rank r holds a[bases[r] .. bases[r+1]) ): NumPy's
+ * pairwise tree depends only on n, so every leaf (<= 128 consecutive elements) is summed by the rank that holds
+ * its first element -- spill-over elements come from halo_dev = float32[G*128], the first 128 elements of every
+ * slab (all-gathered by the caller) -- into slot_dev[gsx_pairwise_slots(n)] (0 elsewhere); the caller all-reduces
+ * (sum, exact: one writer per slot) and gsx_pairwise_finish combines the inner nodes: sq=0 writes meanstd_dev[0] =
+ * mean, sq=1 (after the mean is known) writes meanstd_dev[1] = std.  Bit-identical to gsx_mean_std_f32 on the
+ * concatenated vector.  bases_dev: int64[G+1] on the device. */
+int64_t gsx_pairwise_slots(int64_t n);
+int gsx_pairwise_leaves_dist(const float* a_local_dev, int64_t base, int64_t n_local, int64_t n_global, int32_t sq,
+                             const float* meanstd_dev, const float* halo_dev, const int64_t* bases_dev, int32_t world,
+                             float* slot_dev, void* stream);
+int gsx_pairwise_finish(float* slot_dev, int64_t n_global, int32_t sq, float* meanstd_dev, void* stream);
 
 /* gpu_ops.py:261-263 / data_processor.py:178-180: mask[i] = a[i] < mean + f32(threshold_factor)*std. */
 int gsx_threshold_mask(const float* a_dev, int64_t n, const float* meanstd_dev, float threshold_factor,

@@ -13,7 +13,78 @@ import torch.multiprocessing as mp
 ROOT = Path(__file__).resolve().parent.parent
 
 
-class OracleOps:
+
+def _leaves(n):
+    """Leaves (off, m) of NumPy's float32 pairwise-sum tree over n elements, in offset order."""
+    out = []
+
+    def rec(off, m):
+        if m <= 128:
+            out.append((off, m))
+            return
+        n2 = m // 2
+        n2 -= n2 % 8
+        rec(off, n2)
+        rec(off + n2, m - n2)
+    rec(0, n)
+    return out
+
+
+def _combine(vals, n):
+    """Bottom-up float32 combination of the leaf sums (same tree)."""
+    it = iter(vals)
+
+    def rec(m):
+        if m <= 128:
+            return np.float32(next(it))
+        n2 = m // 2
+        n2 -= n2 % 8
+        a = rec(n2)
+        b = rec(m - n2)
+        return np.float32(a + b)
+    return rec(n)
+
+
+class StatsOpsMixin:
+    """NumPy stand-ins of gsx_pairwise_leaves_dist / gsx_pairwise_finish / threshold (driver logic under test)."""
+
+    def slots(self, n_global):
+        return len(_leaves(n_global))
+
+    def leaves(self, a_local, base, n_global, sq, meanstd, halo, bases_dev, world, slot):
+        a = a_local.numpy()
+        bases = bases_dev.numpy()
+        h = halo.numpy().reshape(world, 128)
+        mean = np.float32(meanstd.numpy()[0])
+        s = slot.numpy()
+        s[:] = 0
+        for i, (off, m) in enumerate(_leaves(n_global)):
+            if not (base <= off < base + len(a)):
+                continue
+            blk = np.empty(m, np.float32)
+            for e in range(m):
+                g = off + e
+                if g < base + len(a):
+                    blk[e] = a[g - base]
+                else:
+                    r = int(np.searchsorted(bases, g, side="right") - 1)
+                    blk[e] = h[r, g - bases[r]]
+            if sq:
+                blk = (blk - mean) * (blk - mean)
+            s[i] = np.add.reduce(blk)
+
+    def finish_stats(self, slot, n_global, sq, meanstd):
+        tot = _combine(slot.numpy(), n_global)
+        v = np.float32(tot / np.float32(n_global))
+        meanstd.numpy()[1 if sq else 0] = np.sqrt(v) if sq else v
+
+    def threshold(self, means_local, meanstd, threshold_factor):
+        ms = meanstd.numpy()
+        thr = np.float32(ms[0] + np.float32(threshold_factor) * ms[1])
+        return torch.from_numpy(means_local.numpy() < thr)
+
+
+class OracleOps(StatsOpsMixin):
     """Stand-in for the CUDA ops so the collective logic can run on CPU."""
 
     def build(self, xyz_all):
@@ -97,6 +168,8 @@ class OracleDensityOps:
     """NumPy stand-in for the CUDA density ops (collective logic under test, CPU/gloo)."""
 
     def minmax(self, xyz):
+        if xyz.shape[0] == 0:
+            return torch.tensor([float("inf")] * 3 + [float("-inf")] * 3, dtype=torch.float32)
         return torch.cat([xyz.min(dim=0).values, xyz.max(dim=0).values])
 
     def voxel_range(self, mm, voxel):
@@ -140,18 +213,20 @@ def _density_worker(rank, world, port, sizes, q):
     dist.destroy_process_group()
 
 
-def test_density_sharded_equals_single():
+@pytest.mark.parametrize("sizes", [(30_000, 20_000), (30_000, 0, 20_000)])
+def test_density_sharded_equals_single(sizes):
+    """Includes a rank with an EMPTY slab: it must take part in every collective (no hang)."""
     import oracle
     from gsx import synth
-    sizes = (30_000, 20_000)
+    world = len(sizes)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 31500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_density_worker, args=(r, 2, port, sizes, q)) for r in range(2)]
+    port = 31500 + (os.getpid() % 2000) + world
+    procs = [ctx.Process(target=_density_worker, args=(r, world, port, sizes, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = {}
-    for _ in range(2):
+    for _ in range(world):
         r, out = q.get(timeout=300)
         res[r] = out
     for p in procs:
@@ -160,13 +235,18 @@ def test_density_sharded_equals_single():
     xyz = synth.xyz(sum(sizes), "mixed")
     for key in res[0]:
         want, info = oracle.density_mask(xyz, sensitivity=key[0], keep_multicluster=key[1])
-        got = np.concatenate([res[0][key][0], res[1][key][0]])
+        got = np.concatenate([res[r][key][0] for r in range(world)])
         assert np.array_equal(got, want), key
-        assert res[0][key][1]["clusters"] == info["clusters"] == res[1][key][1]["clusters"]
+        assert all(res[r][key][1]["clusters"] == info["clusters"] for r in range(world))
 
 
 class OracleBuildOps:
-    """NumPy stand-ins for the three CUDA stages of the distributed grid build (gsx.dist._GsxBuildOps)."""
+    """NumPy stand-ins for the CUDA stages of the distributed grid build (gsx.dist._GsxSorOps)."""
+
+    def minmax(self, xyz_local):
+        if xyz_local.shape[0] == 0:
+            return torch.tensor([float("inf")] * 3 + [float("-inf")] * 3, dtype=torch.float32)
+        return torch.cat([xyz_local.min(dim=0).values, xyz_local.max(dim=0).values])
     P = (73856093, 19349663, 83492791)
 
     def _hash(self, pos, bmin, cell, n_global):
@@ -192,6 +272,8 @@ class OracleBuildOps:
         return torch.from_numpy(pos4), torch.from_numpy(cuts.astype(np.int64))
 
     def merge_into(self, pos4_r, n_global, bmin, cell, out):
+        if pos4_r.shape[0] == 0:
+            return
         p = pos4_r.numpy()
         order = np.argsort(self._hash(p[:, :3], bmin, cell, n_global), kind="stable")
         out.copy_(torch.from_numpy(p[order]))
@@ -226,6 +308,10 @@ class OracleQueryOps(OracleOps):
         out.numpy()[orig[qb:qe]] = md[qb:qe]
 
 
+class OracleDistOps(OracleQueryOps, OracleBuildOps):
+    pass
+
+
 def _dist_build_worker(rank, world, port, sizes, q):
     sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "3dgsconverter_b200"))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -236,17 +322,17 @@ def _dist_build_worker(rank, world, port, sizes, q):
     xyz = synth.xyz(sum(sizes), "mixed")
     off = sum(sizes[:rank])
     local = torch.from_numpy(xyz[off:off + sizes[rank]].copy())
-    mask, means = gd.sor_filter_sharded_v2(local, 16, 2.0, "i64", return_means=True, ops=OracleQueryOps(),
-                                           build_ops=OracleBuildOps())
+    mask, means = gd.sor_filter_distributed(local, 16, 2.0, "i64", return_means=True, ops=OracleDistOps())
     q.put((rank, mask.numpy(), means.numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("sizes", [(15_000, 15_000), (20_000, 9_999), (7_000, 7_000, 7_001)])
+@pytest.mark.parametrize("sizes", [(15_000, 15_000), (20_000, 9_999), (7_000, 7_000, 7_001), (9_000, 0, 100, 5_000)])
 def test_distributed_build_driver_equals_single(sizes):
-    """The host logic of gsx.dist.build_grid_distributed / sor_filter_sharded_v2 (owner partition, all-to-all with
-    split lists, equal and ragged all-gather, query ranges) with NumPy stages: bit-identical to the oracle."""
+    """The host logic of gsx.dist.sor_filter_distributed (one-shot size/box exchange, owner partition, all-to-all with
+    split lists, ragged segment exchange, own-segment queries, routing of the means to the slab owners, distributed
+    NumPy-order statistics; equal, ragged, tiny and EMPTY slabs) with NumPy stages: bit-identical to the oracle."""
     import oracle
     from gsx import synth
     world = len(sizes)

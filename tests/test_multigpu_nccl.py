@@ -11,6 +11,15 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 
 
+def _slab(rank, world, n_per, ragged):
+    """Equal slabs, or ragged ones (rank 0 gets 1/3 more, the last rank the rest) over the same union cloud."""
+    if not ragged:
+        return rank * n_per, (rank + 1) * n_per
+    total = n_per * world
+    cuts = [0] + [min(total, (r + 1) * n_per + n_per // 3) for r in range(world - 1)] + [total]
+    return cuts[rank], cuts[rank + 1]
+
+
 def _worker(rank, world, port, n_per, q):
     sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "3dgsconverter_b200"))
     import torch
@@ -26,8 +35,12 @@ def _worker(rank, world, port, n_per, q):
     for mode in ("i32wrap", "i64"):
         mask, means = gd.sor_filter_sharded(local, 16, 2.0, mode, return_means=True)
         res[f"sor_{mode}"] = (mask.cpu().numpy(), means.cpu().numpy())
-        mask2, means2 = gd.sor_filter_sharded_v2(local, 16, 2.0, mode, return_means=True)
+        mask2, means2 = gd.sor_filter_distributed(local, 16, 2.0, mode, return_means=True)
         res[f"sor2_{mode}"] = (mask2.cpu().numpy(), means2.cpu().numpy())
+        a, b = _slab(rank, world, n_per, True)          # ragged slabs: all-reduce routing, spill-over leaves
+        rag = torch.from_numpy(xyz[a:b].copy()).cuda()
+        mask3, means3 = gd.sor_filter_distributed(rag, 16, 2.0, mode, return_means=True)
+        res[f"sor3_{mode}"] = (mask3.cpu().numpy(), means3.cpu().numpy())
     dm, info = gd.density_filter_sharded(local, sensitivity=0.5, keep_multicluster=True)
     res["density"] = (dm.cpu().numpy(), info["clusters"])
     if rank == 0:  # single-GPU truth on the union cloud
@@ -72,6 +85,10 @@ def test_sharded_equals_single_gpu(gsx_lib):
         gmd2 = np.concatenate([res[r][f"sor2_{mode}"][1] for r in range(world)])
         assert np.array_equal(gmd2.view(np.uint32), tmd.view(np.uint32)), ("distributed build", mode)
         assert np.array_equal(gm2, tm), ("distributed build", mode)
+        gm3 = np.concatenate([res[r][f"sor3_{mode}"][0] for r in range(world)])
+        gmd3 = np.concatenate([res[r][f"sor3_{mode}"][1] for r in range(world)])
+        assert np.array_equal(gmd3.view(np.uint32), tmd.view(np.uint32)), ("distributed build, ragged slabs", mode)
+        assert np.array_equal(gm3, tm), ("distributed build, ragged slabs", mode)
     td, tc = res[0]["truth_density"]
     gd_ = np.concatenate([res[r]["density"][0] for r in range(world)])
     assert np.array_equal(gd_, td) and all(res[r]["density"][1] == tc for r in range(world))
