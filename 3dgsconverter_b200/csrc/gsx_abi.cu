@@ -98,6 +98,17 @@ int gsx_device_sm_count(void) {
 /* ------------------------------------------------------------------ SOR */
 
 int64_t gsx_sor_workspace_bytes(int64_t n) { return sor_workspace_bytes(n); }
+int64_t gsx_sor_grid_workspace_bytes(int64_t n) { return sor_grid_workspace_bytes(n); }
+
+// grid-only functions (build_from_sorted, mean_dists) accept the shorter gsx_sor_grid_workspace_bytes blob
+static int carve_grid_checked(void* ws, int64_t ws_bytes, int64_t n, SorWs& w) {
+    GSX_REQUIRE(n >= 1 && n < 2147483584ll, GSX_ERR_ARG, "sor: n=%lld out of range [1, 2^31-64)", (long long)n);
+    GSX_REQUIRE(ws != nullptr, GSX_ERR_WORKSPACE, "sor: null workspace");
+    w = sor_carve(ws, ws_bytes, n, sor_sort_ws_bytes(n));
+    GSX_REQUIRE(w.grid_ok, GSX_ERR_WORKSPACE, "sor: grid workspace too small (%lld < %zu)", (long long)ws_bytes,
+                w.grid_total);
+    return GSX_OK;
+}
 
 static int carve_checked(void* ws, int64_t ws_bytes, int64_t n, SorWs& w) {
     GSX_REQUIRE(n >= 1 && n < 2147483584ll, GSX_ERR_ARG, "sor: n=%lld out of range [1, 2^31-64)", (long long)n);
@@ -108,10 +119,10 @@ static int carve_checked(void* ws, int64_t ws_bytes, int64_t n, SorWs& w) {
 }
 
 int gsx_sor_minmax(const float* xyz_dev, int64_t n, float* minmax_dev, void* ws, int64_t ws_bytes, void* stream) {
-    SorWs w;
-    int rc = carve_checked(ws, ws_bytes, n, w);
-    if (rc) return rc;
-    return sor_minmax(xyz_dev, n, minmax_dev, w.partial, (cudaStream_t)stream);
+    GSX_REQUIRE(n >= 1, GSX_ERR_ARG, "sor: minmax of an empty cloud");
+    GSX_REQUIRE(ws != nullptr && ws_bytes >= 6 * 1024 * (int64_t)sizeof(float), GSX_ERR_WORKSPACE,
+                "sor: minmax needs 24 KiB of scratch");
+    return sor_minmax(xyz_dev, n, minmax_dev, (float*)ws, (cudaStream_t)stream);  // scratch = the head of ws
 }
 
 /* gpu_ops.py:203-213 with NumPy-2 semantics: extent/vol in float32; vol<=0 -> python float 1.0 (then
@@ -181,7 +192,7 @@ int64_t gsx_sor_spos_offset(int64_t n) {
 int gsx_sor_build_from_sorted(const float* spos4_dev, int64_t n, const float* bmin_host, float cell, void* ws,
                               int64_t ws_bytes, void* stream) {
     SorWs w;
-    int rc = carve_checked(ws, ws_bytes, n, w);
+    int rc = carve_grid_checked(ws, ws_bytes, n, w);
     if (rc) return rc;
     GSX_REQUIRE(cell > 0.f, GSX_ERR_ARG, "sor: cell size must be > 0");
     return sor_build_from_sorted((const float4*)spos4_dev, n, bmin_host, cell, w, (cudaStream_t)stream);
@@ -191,7 +202,7 @@ int gsx_sor_mean_dists_range(int64_t n, int64_t q_begin, int64_t q_end, int32_t 
                              const float* bmin_host, float cell, void* ws, int64_t ws_bytes, float* final_means_dev,
                              unsigned long long* stats_dev, void* stream) {
     SorWs w;
-    int rc = carve_checked(ws, ws_bytes, n, w);
+    int rc = carve_grid_checked(ws, ws_bytes, n, w);
     if (rc) return rc;
     return sor_mean_dists(w, q_begin, q_end, k, hash_mode, bmin_host, cell, final_means_dev, stats_dev,
                           (cudaStream_t)stream);

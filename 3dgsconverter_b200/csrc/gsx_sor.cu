@@ -58,14 +58,12 @@ constexpr int kQueryBatch = GSX_QUERY_BATCH;   // consecutive queries grabbed pe
 // ------------------------------------------------------------------ workspace layout
 
 SorWs sor_carve(void* ws, int64_t ws_bytes, int64_t n, size_t sort_ws_bytes) {
+    // The GRID part (what the query kernel reads) comes first, so a blob of gsx_sor_grid_workspace_bytes(n) is a
+    // valid workspace for build_from_sorted / mean_dists; the sort buffers (keys, values, radix scratch) follow.
     SorWs w;
     Carver c(ws, (size_t)ws_bytes);
     int64_t nchunk = (n + 31) / 32, nsuper = (nchunk + 31) / 32;
     w.n = n;
-    w.keys0 = c.take<uint64_t>(n);
-    w.keys1 = c.take<uint64_t>(n);
-    w.vals0 = c.take<int32_t>(n);
-    w.vals1 = c.take<int32_t>(n);
     w.spos = c.take<float4>(n);
     w.tab_se = c.take<int2>(n);
     w.tab_box = c.take<float4>(2 * n);
@@ -77,12 +75,18 @@ SorWs sor_carve(void* ws, int64_t ws_bytes, int64_t n, size_t sort_ws_bytes) {
     w.counters = c.take<unsigned int>(64);
     w.stats = c.take<unsigned long long>(8);
     w.meanstd = c.take<float>(8);
-    w.sort_ws_bytes = sort_ws_bytes;
-    w.sort_ws = c.take<char>(sort_ws_bytes);
     w.ms_bytes = mean_std_ws_bytes(n);
     w.ms_ws = c.take<char>(w.ms_bytes);
+    w.grid_total = align_up(c.off, 256);
+    w.keys0 = c.take<uint64_t>(n);
+    w.keys1 = c.take<uint64_t>(n);
+    w.vals0 = c.take<int32_t>(n);
+    w.vals1 = c.take<int32_t>(n);
+    w.sort_ws_bytes = sort_ws_bytes;
+    w.sort_ws = c.take<char>(sort_ws_bytes);
     w.total = align_up(c.off, 256);
     w.ok = c.ok();
+    w.grid_ok = w.grid_total <= (size_t)(ws_bytes > 0 ? ws_bytes : 0);
     return w;
 }
 
@@ -92,6 +96,12 @@ int64_t sor_workspace_bytes(int64_t n) {
     if (n < 1) n = 1;
     SorWs w = sor_carve(nullptr, 0, n, sor_sort_ws_bytes(n));
     return (int64_t)w.total + 1024;
+}
+
+int64_t sor_grid_workspace_bytes(int64_t n) {
+    if (n < 1) n = 1;
+    SorWs w = sor_carve(nullptr, 0, n, sor_sort_ws_bytes(n));
+    return (int64_t)w.grid_total;
 }
 
 // ------------------------------------------------------------------ min / max

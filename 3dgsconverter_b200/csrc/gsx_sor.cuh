@@ -26,12 +26,13 @@ struct SorWs {
     size_t sort_ws_bytes;
     char* ms_ws;
     size_t ms_bytes;
-    size_t total;
-    bool ok;
+    size_t total, grid_total;  // whole workspace / the grid part only (a prefix)
+    bool ok, grid_ok;
 };
 
 SorWs sor_carve(void* ws, int64_t ws_bytes, int64_t n, size_t sort_ws_bytes);
 int64_t sor_workspace_bytes(int64_t n);
+int64_t sor_grid_workspace_bytes(int64_t n);
 size_t sor_sort_ws_bytes(int64_t n);
 int sor_minmax(const float* xyz, int64_t n, float* minmax_dev, float* partial, cudaStream_t st);
 int sor_build(const float* xyz, int64_t n, const float* bmin, float cell, SorWs& w, cudaStream_t st);

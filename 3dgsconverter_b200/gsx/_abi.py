@@ -35,6 +35,7 @@ _SIGS = {
     "gsx_device_sm_count": (C.c_int, []),
     "gsx_kernel_launches": (C.c_longlong, []),
     "gsx_sor_workspace_bytes": (_i64, [_i64]),
+    "gsx_sor_grid_workspace_bytes": (_i64, [_i64]),
     "gsx_sor_minmax": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp]),
     "gsx_sor_cell_size": (C.c_float, [_f32p, _i64]),
     "gsx_sor_build": (C.c_int, [_vp, _i64, _f32p, C.c_float, _vp, _i64, _vp]),

@@ -113,7 +113,7 @@ class _GsxSorOps:
         n = xyz_local.shape[0]
         if n == 0:
             return torch.tensor([float("inf")] * 3 + [float("-inf")] * 3, dtype=torch.float32, device=dev)
-        ws = sor.workspace(1, dev)  # the reduction scratch is independent of n
+        ws = torch.empty(32768, dtype=torch.uint8, device=dev)  # reduction scratch (24 KiB)
         out = torch.empty(8, dtype=torch.float32, device=dev)
         check(lib.gsx_sor_minmax(_ptr(xyz_local), n, _ptr(out), _ptr(ws), ws.numel(), _stream()), "gsx_sor_minmax")
         return out[:6]
@@ -154,9 +154,8 @@ class _GsxSorOps:
 
     def new_grid_storage(self, n_global, dev):
         """Workspace of the final grid and a [n_global,4] view of its sorted-position array (exchange target)."""
-        from . import sor
         from ._abi import lib
-        ws = sor.workspace(n_global, dev)
+        ws = torch.empty(lib.gsx_sor_grid_workspace_bytes(n_global), dtype=torch.uint8, device=dev)  # no sort buffers
         off = lib.gsx_sor_spos_offset(n_global)
         return ws, ws[off: off + n_global * 16].view(torch.float32).view(n_global, 4)
 

@@ -42,10 +42,15 @@ long long gsx_kernel_launches(void); /* cumulative number of gsx kernels launche
 
 /* ---- SOR, Taichi semantics: gpu_ops.py:193-263 (filter_sor_gpu) + :98-176 (kernel) - */
 
-/* Scratch needed by gsx_sor_filter_device / the gsx_sor_* stages for n points. */
+/* Scratch needed by gsx_sor_filter_device / the gsx_sor_* stages for n points.  The grid the query kernel reads
+ * (sorted positions, bucket table, boxes) is a PREFIX of that blob: gsx_sor_build_from_sorted and
+ * gsx_sor_mean_dists[_range] also accept a blob of only gsx_sor_grid_workspace_bytes(n) (no sort buffers) -- what
+ * every rank of the distributed build holds for the union cloud. */
 int64_t gsx_sor_workspace_bytes(int64_t n);
+int64_t gsx_sor_grid_workspace_bytes(int64_t n);
 
-/* gpu_ops.py:203-204: per-axis min/max of xyz[n,3] -> minmax_dev[6] = {minx,miny,minz,maxx,maxy,maxz}. */
+/* gpu_ops.py:203-204: per-axis min/max of xyz[n,3] -> minmax_dev[6] = {minx,miny,minz,maxx,maxy,maxz}.
+ * Scratch: the first 24 KiB of ws (any workspace of gsx_sor_workspace_bytes, or a small blob of its own). */
 int gsx_sor_minmax(const float* xyz_dev, int64_t n, float* minmax_dev, void* ws, int64_t ws_bytes, void* stream);
 
 /* gpu_ops.py:205-213 on the host (NumPy-2 float32 semantics, powf).  minmax is a HOST array of 6. */
