@@ -462,4 +462,42 @@ int gsx_kmeans_host(const float* X_host, int64_t n, int32_t K, int32_t D, int32_
     return GSX_OK;
 }
 
+/* SOG shN schedule in one call on HOST buffers: nprob problems stored back to back in X_host (rows row_off[p] ..
+ * row_off[p+1]), each with K centroids; C_host_inout [nprob*K*D] holds the init on entry, the centroids on return. */
+int gsx_kmeans_host_batched(const float* X_host, const int64_t* row_off_host, int32_t nprob, int32_t K, int32_t D,
+                            int32_t max_iter, float* C_host_inout, int32_t* labels_host, int32_t assign_mode) {
+    GSX_REQUIRE(nprob >= 1 && K >= 1 && D >= 1, GSX_ERR_ARG, "kmeans: bad shape");
+    GSX_REQUIRE(row_off_host[0] == 0, GSX_ERR_ARG, "kmeans: row_off[0] must be 0");
+    const int64_t n = row_off_host[nprob];
+    GSX_REQUIRE(n >= 1, GSX_ERR_ARG, "kmeans: no rows");
+    cudaStream_t st = 0;
+    DevBuf X(st), C(st), L(st), cnt(st), ws(st);
+    int rc;
+    int64_t wsb = kmeans_workspace_bytes(n, nprob, K, D);
+    if ((rc = X.alloc((size_t)n * D * 4))) return rc;
+    if ((rc = C.alloc((size_t)nprob * K * D * 4))) return rc;
+    if ((rc = L.alloc((size_t)n * 4))) return rc;
+    if ((rc = cnt.alloc((size_t)nprob * K * 4))) return rc;
+    if ((rc = ws.alloc((size_t)wsb))) return rc;
+    GSX_CUDA_CHECK(cudaMemcpyAsync(X.p, X_host, (size_t)n * D * 4, cudaMemcpyHostToDevice, st));
+    GSX_CUDA_CHECK(cudaMemcpyAsync(C.p, C_host_inout, (size_t)nprob * K * D * 4, cudaMemcpyHostToDevice, st));
+    GSX_CUDA_CHECK(cudaMemsetAsync(L.p, 0, (size_t)n * 4, st));
+    if ((rc = kmeans_lloyd((const float*)X.p, row_off_host, nprob, K, D, max_iter, (float*)C.p, (int*)L.p, (int*)cnt.p,
+                           ws.p, wsb, assign_mode, nullptr, st)))
+        return rc;
+    GSX_CUDA_CHECK(cudaMemcpyAsync(C_host_inout, C.p, (size_t)nprob * K * D * 4, cudaMemcpyDeviceToHost, st));
+    GSX_CUDA_CHECK(cudaMemcpyAsync(labels_host, L.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    GSX_CUDA_CHECK(cudaStreamSynchronize(st));
+    return GSX_OK;
+}
+
+/* free / total device memory of the current device (sizing decisions of the host-buffer entry points) */
+int gsx_device_memory(int64_t* free_bytes, int64_t* total_bytes) {
+    size_t f = 0, t = 0;
+    GSX_CUDA_CHECK(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = (int64_t)f;
+    if (total_bytes) *total_bytes = (int64_t)t;
+    return GSX_OK;
+}
+
 }  // extern "C"

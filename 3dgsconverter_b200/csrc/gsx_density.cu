@@ -197,6 +197,78 @@ __global__ void k_vox_dense_counts_hash(const long long* __restrict__ dense_vox,
     dense_cnt[t] = hcnt[s];
 }
 
+// Wide-key variant for voxel boxes that span 2^21 or more voxels on some axis (one far-away flyer with a small voxel):
+// the slot key is the pair a = (rx << 32 | ry) + 1, b = rz + 1 (extents < 2^31).  A slot is claimed by a CAS on `a`;
+// the owner then publishes `b`; a thread that finds its own `a` waits for `b` (independent thread scheduling makes
+// the intra-warp wait safe) and moves on if it differs (same x,y column, other z).  Exact for any extent < 2^31.
+__device__ __forceinline__ void wide_key(long long rx, long long ry, long long rz, unsigned long long& a,
+                                         unsigned long long& b) {
+    a = (((unsigned long long)rx << 32) | (unsigned long long)ry) + 1ull;
+    b = (unsigned long long)rz + 1ull;
+}
+
+__device__ __forceinline__ uint64_t wide_find_or_insert(unsigned long long a, unsigned long long b,
+                                                        unsigned long long* ha, unsigned long long* hb,
+                                                        uint64_t slot_mask, bool insert) {
+    uint64_t s = mix64(a ^ mix64(b)) & slot_mask;
+    for (;;) {
+        unsigned long long cur = *((volatile unsigned long long*)(ha + s));
+        if (cur == 0ull) {
+            if (!insert) return ~0ull;
+            unsigned long long prev = atomicCAS(ha + s, 0ull, a);
+            if (prev == 0ull) {
+                atomicExch(hb + s, b);
+                return s;
+            }
+            cur = prev;
+        }
+        if (cur == a) {
+            unsigned long long bv;
+            do {
+                bv = *((volatile unsigned long long*)(hb + s));
+            } while (bv == 0ull);
+            if (bv == b) return s;
+        }
+        s = (s + 1) & slot_mask;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_vox_count_hash_wide(const float* __restrict__ xyz, int64_t n, float voxel,
+                                                             VoxGrid g, int thr, unsigned long long* ha,
+                                                             unsigned long long* hb, int* hcnt, uint64_t slot_mask,
+                                                             unsigned long long* __restrict__ counters,
+                                                             long long* __restrict__ dense_vox, int64_t cap) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long qx = voxel_of(xyz[3 * i], voxel), qy = voxel_of(xyz[3 * i + 1], voxel),
+              qz = voxel_of(xyz[3 * i + 2], voxel);
+    unsigned long long a, b;
+    wide_key(qx - g.q0[0], qy - g.q0[1], qz - g.q0[2], a, b);
+    uint64_t s = wide_find_or_insert(a, b, ha, hb, slot_mask, true);
+    int old = atomicAdd(hcnt + s, 1);
+    if (old == 0) atomicAdd(counters + 1, 1ull);
+    if (old + 1 == thr) {
+        unsigned long long slot = atomicAdd(counters, 1ull);
+        if ((int64_t)slot < cap) {
+            dense_vox[3 * slot] = qx;
+            dense_vox[3 * slot + 1] = qy;
+            dense_vox[3 * slot + 2] = qz;
+        }
+    }
+}
+
+__global__ void k_vox_dense_counts_hash_wide(const long long* __restrict__ dense_vox, int64_t nd, VoxGrid g,
+                                             unsigned long long* ha, unsigned long long* hb,
+                                             const int* __restrict__ hcnt, uint64_t slot_mask,
+                                             int* __restrict__ dense_cnt) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nd) return;
+    unsigned long long a, b;
+    wide_key(dense_vox[3 * t] - g.q0[0], dense_vox[3 * t + 1] - g.q0[1], dense_vox[3 * t + 2] - g.q0[2], a, b);
+    uint64_t s = wide_find_or_insert(a, b, ha, hb, slot_mask, false);
+    dense_cnt[t] = s == ~0ull ? 0 : hcnt[s];
+}
+
 int density_voxel_count(const float* xyz, int64_t n, float voxel, int64_t min_points, int64_t* dense_vox_host,
                         int32_t* dense_cnt_host, int64_t cap, int64_t* n_dense_host, int64_t* n_voxels_host, void* ws,
                         int64_t ws_bytes, cudaStream_t st) {
@@ -223,12 +295,14 @@ int density_voxel_count(const float* xyz, int64_t n, float voxel, int64_t min_po
     GSX_CUDA_CHECK(cudaStreamSynchronize(st));
     VoxGrid g;
     double cells = 1.0;
+    bool wide = false;
     for (int a = 0; a < 3; ++a) {
         g.q0[a] = voxel_of(mm[a], voxel);  // floor(x/voxel) is monotone in x: min/max commute with it
         long long q1 = voxel_of(mm[3 + a], voxel);
         g.dim[a] = q1 - g.q0[a] + 1;
-        GSX_REQUIRE(g.dim[a] >= 1 && g.dim[a] < kAxisLim, GSX_ERR_UNSUPPORTED,
-                    "density: voxel grid extent %lld on axis %d exceeds 2^21", g.dim[a], a);
+        GSX_REQUIRE(g.dim[a] >= 1 && g.dim[a] < (1ll << 31), GSX_ERR_UNSUPPORTED,
+                    "density: voxel grid extent %lld on axis %d exceeds 2^31 voxels", g.dim[a], a);
+        if (g.dim[a] >= kAxisLim) wide = true;  // the packed 3 x 21-bit key does not fit: two-word keys
         cells *= (double)g.dim[a];
     }
     long long thr_ll = min_points < 1 ? 1 : min_points;
@@ -239,6 +313,7 @@ int density_voxel_count(const float* xyz, int64_t n, float voxel, int64_t min_po
     bool use_grid = cells * 4.0 <= (double)blob_bytes;
     uint64_t slot_mask = 0;
     unsigned long long* hkeys = nullptr;
+    unsigned long long* hkeys_b = nullptr;
     int* hcnt = nullptr;
     if (use_grid) {
         size_t ncell = (size_t)g.dim[0] * g.dim[1] * g.dim[2];
@@ -256,8 +331,18 @@ int density_voxel_count(const float* xyz, int64_t n, float voxel, int64_t min_po
         hkeys = (unsigned long long*)blob;
         hcnt = (int*)(blob + slots * 8);
         slot_mask = slots - 1;
-        GSX_CUDA_CHECK(cudaMemsetAsync(blob, 0, slots * 12, st));
-        k_vox_count_hash<<<blocks, 256, 0, st>>>(xyz, n, voxel, g, thr, hkeys, hcnt, slot_mask, counters, dvox, cap);
+        if (!wide) {
+            GSX_CUDA_CHECK(cudaMemsetAsync(blob, 0, slots * 12, st));
+            k_vox_count_hash<<<blocks, 256, 0, st>>>(xyz, n, voxel, g, thr, hkeys, hcnt, slot_mask, counters, dvox, cap);
+        } else {  // two-word keys in the same budget: half the slots (still >= n), 20 bytes each
+            slots >>= 1;
+            hkeys_b = hkeys + slots;
+            hcnt = (int*)(blob + slots * 16);
+            slot_mask = slots - 1;
+            GSX_CUDA_CHECK(cudaMemsetAsync(blob, 0, slots * 20, st));
+            k_vox_count_hash_wide<<<blocks, 256, 0, st>>>(xyz, n, voxel, g, thr, hkeys, hkeys_b, hcnt, slot_mask,
+                                                          counters, dvox, cap);
+        }
     }
     GSX_KERNEL_CHECK();
     unsigned long long hc[2];
@@ -271,7 +356,8 @@ int density_voxel_count(const float* xyz, int64_t n, float voxel, int64_t min_po
     if (nd > 0) {
         int b2 = (int)((nd + 127) / 128);
         if (use_grid) k_vox_dense_counts_grid<<<b2, 128, 0, st>>>(dvox, nd, g, (const int*)blob, dcnt);
-        else k_vox_dense_counts_hash<<<b2, 128, 0, st>>>(dvox, nd, g, hkeys, hcnt, slot_mask, dcnt);
+        else if (!wide) k_vox_dense_counts_hash<<<b2, 128, 0, st>>>(dvox, nd, g, hkeys, hcnt, slot_mask, dcnt);
+        else k_vox_dense_counts_hash_wide<<<b2, 128, 0, st>>>(dvox, nd, g, hkeys, hkeys_b, hcnt, slot_mask, dcnt);
         GSX_KERNEL_CHECK();
         GSX_CUDA_CHECK(cudaMemcpyAsync(dense_vox_host, dvox, (size_t)nd * 24, cudaMemcpyDeviceToHost, st));
         GSX_CUDA_CHECK(cudaMemcpyAsync(dense_cnt_host, dcnt, (size_t)nd * 4, cudaMemcpyDeviceToHost, st));
@@ -324,7 +410,7 @@ static int make_grid(const int64_t* q0, const int64_t* dim, VoxGrid& g, size_t& 
     for (int a = 0; a < 3; ++a) {
         g.q0[a] = q0[a];
         g.dim[a] = dim[a];
-        GSX_REQUIRE(dim[a] >= 1 && dim[a] < kAxisLim, GSX_ERR_ARG, "density: bad grid extent on axis %d", a);
+        GSX_REQUIRE(dim[a] >= 1, GSX_ERR_ARG, "density: bad grid extent on axis %d", a);
         cells *= (double)dim[a];
     }
     GSX_REQUIRE(cells < 4.0e9, GSX_ERR_UNSUPPORTED, "density: grid too large for the dense path");
@@ -387,10 +473,23 @@ int density_grid_dense(const int* grid_dev, const int64_t* q0, const int64_t* di
 }
 
 // ---------------------------------------------------------------- membership mask
+template <bool WIDE>
 __device__ __forceinline__ uint8_t vox_member_one(float x, float y, float z, float voxel, long long ox,
                                                   long long oy, long long oz,
                                                   const unsigned long long* __restrict__ set, uint64_t slot_mask) {
     long long rx = voxel_of(x, voxel) - ox, ry = voxel_of(y, voxel) - oy, rz = voxel_of(z, voxel) - oz;
+    if (WIDE) {  // two-word keys {a, b} at set[2s], set[2s+1]: kept voxels that span >= 2^21 on some axis
+        if (rx < 0 || ry < 0 || rz < 0 || rx >= (1ll << 31) || ry >= (1ll << 31) || rz >= (1ll << 31)) return 0;
+        unsigned long long a, b;
+        wide_key(rx, ry, rz, a, b);
+        uint64_t s = mix64(a ^ mix64(b)) & slot_mask;
+        for (;;) {
+            unsigned long long ca = __ldg(set + 2 * s);
+            if (ca == 0ull) return 0;
+            if (ca == a && __ldg(set + 2 * s + 1) == b) return 1;
+            s = (s + 1) & slot_mask;
+        }
+    }
     if (rx < 0 || ry < 0 || rz < 0 || rx >= kAxisLim || ry >= kAxisLim || rz >= kAxisLim) return 0;
     uint64_t key = pack_rel(rx, ry, rz);
     uint64_t s = mix64(key) & slot_mask;
@@ -402,16 +501,18 @@ __device__ __forceinline__ uint8_t vox_member_one(float x, float y, float z, flo
     }
 }
 
+template <bool WIDE>
 __global__ void __launch_bounds__(256) k_vox_member(const float* __restrict__ xyz, int64_t begin, int64_t n,
                                                     float voxel, long long ox, long long oy, long long oz,
                                                     const unsigned long long* __restrict__ set, uint64_t slot_mask,
                                                     uint8_t* __restrict__ mask) {
     int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    mask[i] = vox_member_one(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], voxel, ox, oy, oz, set, slot_mask);
+    mask[i] = vox_member_one<WIDE>(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], voxel, ox, oy, oz, set, slot_mask);
 }
 
 // 4 points (3 x 128-bit loads) per thread, uchar4 store
+template <bool WIDE>
 __global__ void __launch_bounds__(256) k_vox_member4(const float4* __restrict__ xyz4, int64_t n4, float voxel,
                                                      long long ox, long long oy, long long oz,
                                                      const unsigned long long* __restrict__ set, uint64_t slot_mask,
@@ -420,10 +521,10 @@ __global__ void __launch_bounds__(256) k_vox_member4(const float4* __restrict__ 
     if (t >= n4) return;
     float4 a = ld_stream_f4(xyz4 + 3 * t), b = ld_stream_f4(xyz4 + 3 * t + 1), c = ld_stream_f4(xyz4 + 3 * t + 2);
     uchar4 o;
-    o.x = vox_member_one(a.x, a.y, a.z, voxel, ox, oy, oz, set, slot_mask);
-    o.y = vox_member_one(a.w, b.x, b.y, voxel, ox, oy, oz, set, slot_mask);
-    o.z = vox_member_one(b.z, b.w, c.x, voxel, ox, oy, oz, set, slot_mask);
-    o.w = vox_member_one(c.y, c.z, c.w, voxel, ox, oy, oz, set, slot_mask);
+    o.x = vox_member_one<WIDE>(a.x, a.y, a.z, voxel, ox, oy, oz, set, slot_mask);
+    o.y = vox_member_one<WIDE>(a.w, b.x, b.y, voxel, ox, oy, oz, set, slot_mask);
+    o.z = vox_member_one<WIDE>(b.z, b.w, c.x, voxel, ox, oy, oz, set, slot_mask);
+    o.w = vox_member_one<WIDE>(c.y, c.z, c.w, voxel, ox, oy, oz, set, slot_mask);
     mask4[t] = o;
 }
 
@@ -441,34 +542,49 @@ int density_member_mask(const float* xyz, int64_t n, float voxel, const int64_t*
             if (keep[3 * t + a] < o[a]) o[a] = keep[3 * t + a];
             if (keep[3 * t + a] > hi[a]) hi[a] = keep[3 * t + a];
         }
-    for (int a = 0; a < 3; ++a)
-        GSX_REQUIRE(hi[a] - o[a] < kAxisLim, GSX_ERR_UNSUPPORTED, "density: kept voxels span more than 2^21 on axis %d", a);
+    bool wide = false;
+    for (int a = 0; a < 3; ++a) {
+        GSX_REQUIRE(hi[a] - o[a] < (1ll << 31), GSX_ERR_UNSUPPORTED, "density: kept voxels span more than 2^31 on axis %d", a);
+        if (hi[a] - o[a] >= kAxisLim) wide = true;
+    }
     size_t slots = 64;
     while (slots < (size_t)2 * n_keep) slots <<= 1;
-    GSX_REQUIRE(slots * 8 <= (size_t)ws_bytes, GSX_ERR_WORKSPACE, "density: workspace too small for the keep set");
-    std::vector<unsigned long long> tab(slots, 0ull);
+    const size_t words = wide ? 2 : 1;
+    GSX_REQUIRE(slots * 8 * words <= (size_t)ws_bytes, GSX_ERR_WORKSPACE, "density: workspace too small for the keep set");
+    std::vector<unsigned long long> tab(slots * words, 0ull);
     for (int64_t t = 0; t < n_keep; ++t) {
-        uint64_t key = ((((uint64_t)(keep[3 * t] - o[0])) << (2 * kAxisBits)) |
-                        (((uint64_t)(keep[3 * t + 1] - o[1])) << kAxisBits) | (uint64_t)(keep[3 * t + 2] - o[2])) + 1ull;
-        uint64_t s = mix64_host(key) & (slots - 1);
-        while (tab[s] != 0ull && tab[s] != key) s = (s + 1) & (slots - 1);
-        tab[s] = key;
+        const uint64_t rx = (uint64_t)(keep[3 * t] - o[0]), ry = (uint64_t)(keep[3 * t + 1] - o[1]),
+                       rz = (uint64_t)(keep[3 * t + 2] - o[2]);
+        if (!wide) {
+            uint64_t key = ((rx << (2 * kAxisBits)) | (ry << kAxisBits) | rz) + 1ull;
+            uint64_t s = mix64_host(key) & (slots - 1);
+            while (tab[s] != 0ull && tab[s] != key) s = (s + 1) & (slots - 1);
+            tab[s] = key;
+        } else {
+            uint64_t a = ((rx << 32) | ry) + 1ull, b = rz + 1ull;
+            uint64_t s = mix64_host(a ^ mix64_host(b)) & (slots - 1);
+            while (tab[2 * s] != 0ull && !(tab[2 * s] == a && tab[2 * s + 1] == b)) s = (s + 1) & (slots - 1);
+            tab[2 * s] = a;
+            tab[2 * s + 1] = b;
+        }
     }
-    GSX_CUDA_CHECK(cudaMemcpyAsync(ws, tab.data(), slots * 8, cudaMemcpyHostToDevice, st));
+    GSX_CUDA_CHECK(cudaMemcpyAsync(ws, tab.data(), slots * 8 * words, cudaMemcpyHostToDevice, st));
     GSX_CUDA_CHECK(cudaStreamSynchronize(st));  // tab is a stack-owned pageable buffer
+    const unsigned long long* set = (const unsigned long long*)ws;
     int64_t n4 = 0;
     if (((uintptr_t)xyz % 16 == 0) && ((uintptr_t)mask % 4 == 0)) {
         n4 = n / 4;
         if (n4 > 0) {
-            k_vox_member4<<<(int)((n4 + 255) / 256), 256, 0, st>>>((const float4*)xyz, n4, voxel, o[0], o[1], o[2],
-                                                                    (const unsigned long long*)ws, slots - 1,
-                                                                    (uchar4*)mask);
+            const int b4 = (int)((n4 + 255) / 256);
+            if (wide) k_vox_member4<true><<<b4, 256, 0, st>>>((const float4*)xyz, n4, voxel, o[0], o[1], o[2], set, slots - 1, (uchar4*)mask);
+            else k_vox_member4<false><<<b4, 256, 0, st>>>((const float4*)xyz, n4, voxel, o[0], o[1], o[2], set, slots - 1, (uchar4*)mask);
             GSX_KERNEL_CHECK();
         }
     }
     if (n - 4 * n4 > 0) {
-        k_vox_member<<<(int)((n - 4 * n4 + 255) / 256), 256, 0, st>>>(xyz, 4 * n4, n, voxel, o[0], o[1], o[2],
-                                                                      (const unsigned long long*)ws, slots - 1, mask);
+        const int b1 = (int)((n - 4 * n4 + 255) / 256);
+        if (wide) k_vox_member<true><<<b1, 256, 0, st>>>(xyz, 4 * n4, n, voxel, o[0], o[1], o[2], set, slots - 1, mask);
+        else k_vox_member<false><<<b1, 256, 0, st>>>(xyz, 4 * n4, n, voxel, o[0], o[1], o[2], set, slots - 1, mask);
         GSX_KERNEL_CHECK();
     }
     return GSX_OK;

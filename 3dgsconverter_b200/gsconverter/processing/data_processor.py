@@ -12,6 +12,11 @@ indices.  With ``DataProcessor.defer_compaction = True`` (what ``gsx.dropin.patc
 for converter.py, which ignores the filters' return values and reads ``processor.data`` once,
 converter.py:259) that host gather happens ONCE, when ``.data`` is read, and the filters return None.
 
+Constraint of the cached working set: the xyz / opacity columns are uploaded when the first filter runs and stay
+in HBM; in-place edits of ``dp.data['x']`` (etc.) BETWEEN two filters are not seen by the later filter -- assign
+``dp.data = new_array`` (the setter drops the device copy) or call ``dp.invalidate()`` after such an edit.  The
+reference re-reads ``self.data`` in every filter; converter.py never edits coordinates between filters.
+
 No CPU fallback: if the CUDA backend is unavailable the filters raise instead of silently running
 the reference's SciPy path (whose mask the reference computes and then discards -- SURVEY F5).
 """
@@ -55,6 +60,11 @@ class DataProcessor:
         self._chain = None
         self._pending = False
 
+    def invalidate(self):
+        """Drop the device-resident columns (call after editing coordinates / opacity of ``.data`` in place)."""
+        _ = self.data          # gathers pending survivors first
+        self._chain = None
+
     def _working_set(self):
         _require_backend()
         if self._chain is None:
@@ -78,6 +88,7 @@ class DataProcessor:
         debug_print("[DEBUG] Executing 'apply_density_filter' function...")
         if not isinstance(self._data, np.ndarray):
             raise TypeError("self.data must be a numpy structured array.")
+        _require_backend()   # imports .gpu_ops first: that module puts GSX_HOME on sys.path (file-copy integration)
         from gsx import density
         if sensitivity is not None:
             voxel_size, threshold_percentage = density.slider(sensitivity)

@@ -80,6 +80,8 @@ _SIGS = {
     "gsx_kmeans_tensor_core_supported": (_i32, [_i32, _i32]),
     "gsx_kmeans_tc_debug_scores": (C.c_int, [_vp, _i64, _vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
     "gsx_kmeans_host": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _vp, _vp, _i32]),
+    "gsx_kmeans_host_batched": (C.c_int, [_vp, C.POINTER(_i64), _i32, _i32, _i32, _i32, _vp, _vp, _i32]),
+    "gsx_device_memory": (C.c_int, [C.POINTER(_i64), C.POINTER(_i64)]),
 }
 
 for _name, (_res, _args) in _SIGS.items():

@@ -86,7 +86,7 @@ def member_mask(xyz: torch.Tensor, voxel_size: float, keep_vox: np.ndarray, ws: 
     _check_xyz(xyz)
     n = xyz.shape[0]
     keep_vox = np.ascontiguousarray(keep_vox, dtype=np.int64).reshape(-1, 3)
-    need = max(64, 1 << int(np.ceil(np.log2(max(2 * len(keep_vox), 1))))) * 8 + 256
+    need = max(64, 1 << int(np.ceil(np.log2(max(2 * len(keep_vox), 1))))) * 16 + 256   # two-word keys if far apart
     if ws is None or ws.numel() < need:
         ws = torch.empty(need, dtype=torch.uint8, device=xyz.device)
     mask = torch.empty(n, dtype=torch.uint8, device=xyz.device)

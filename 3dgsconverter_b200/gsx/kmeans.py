@@ -74,3 +74,24 @@ def kmeans_host(data: np.ndarray, K: int, max_iter: int, init: np.ndarray, assig
                               labels.ctypes.data_as(C.c_void_p), KM_ASSIGN[assign or default_assign_mode()]),
           "gsx_kmeans_host")
     return Cc, labels
+
+
+def kmeans_host_batched(base: np.ndarray, row_off, K: int, max_iter: int, init: np.ndarray, assign: str | None = None):
+    """Host-buffer entry for several problems stored back to back in `base` [N,D] (the SOG shN chunk schedule):
+    one upload, one batched launch per phase.  init float32 [nprob,K,D].  Returns (C [nprob,K,D], labels int32[N])."""
+    X = np.ascontiguousarray(base, dtype=np.float32)
+    row_off = np.ascontiguousarray(row_off, dtype=np.int64)
+    nprob = len(row_off) - 1
+    D = X.shape[1]
+    Cc = np.ascontiguousarray(init, dtype=np.float32).reshape(nprob, K, D).copy()
+    labels = np.zeros(int(row_off[-1]), dtype=np.int32)
+    check(lib.gsx_kmeans_host_batched(X.ctypes.data_as(C.c_void_p), row_off.ctypes.data_as(C.POINTER(C.c_int64)), nprob, K,
+                                      D, max_iter, Cc.ctypes.data_as(C.c_void_p), labels.ctypes.data_as(C.c_void_p),
+                                      KM_ASSIGN[assign or default_assign_mode()]), "gsx_kmeans_host_batched")
+    return Cc, labels
+
+
+def device_free_bytes() -> int:
+    f, t = C.c_int64(0), C.c_int64(0)
+    check(lib.gsx_device_memory(C.byref(f), C.byref(t)), "gsx_device_memory")
+    return int(f.value)

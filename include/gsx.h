@@ -233,6 +233,15 @@ int gsx_kmeans_tc_debug_scores(const float* X_dev, int64_t rows, const float* C_
 int gsx_kmeans_host(const float* X_host, int64_t n, int32_t K, int32_t D, int32_t max_iter, float* C_host_inout,
                     int32_t* labels_host, int32_t assign_mode);
 
+/* The SOG shN schedule (formats/sog.py:536-549: up to 64 chunks of one SH block, each clustered by its own
+ * gpu_ops.kmeans call) in ONE call on HOST buffers: one upload of the block, one batched launch per phase.
+ * nprob problems back to back in X_host (rows row_off[p] .. row_off[p+1]), K centroids each;
+ * C_host_inout float32[nprob*K*D]: the init rows on entry, the centroids on return; labels_host int32[n]. */
+int gsx_kmeans_host_batched(const float* X_host, const int64_t* row_off_host, int32_t nprob, int32_t K, int32_t D,
+                            int32_t max_iter, float* C_host_inout, int32_t* labels_host, int32_t assign_mode);
+/* Free / total memory of the current device, for the sizing decisions of the host-buffer callers. */
+int gsx_device_memory(int64_t* free_bytes, int64_t* total_bytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,6 +88,23 @@ def test_density_explicit_params_and_hash_path(cuda, gsx_lib):
         assert np.array_equal(got.cpu().numpy(), want), (vs, thr, multi)
 
 
+def test_density_huge_extent_wide_keys(cuda, gsx_lib):
+    """a distant flyer with a small voxel spans >= 2^21 voxels per axis -- the reference (np.unique on int64
+    triples) handles any extent; the hash path switches to two-word keys instead of failing."""
+    import torch
+    import oracle
+    from gsx import density
+    rng = np.random.default_rng(5)
+    core = rng.normal(0, 1, (30_000, 3))
+    far_clump = rng.normal(0, 0.02, (3_000, 3)) + np.array([1e7, -1e7, 1e7])   # dense, 1e8 voxels away at voxel 0.1
+    xyz = np.r_[core, far_clump, np.array([[1e7, 1e7, 1e7], [-3e6, 0, 0]])].astype(np.float32)
+    for vs, thr, multi in ((0.1, 0.01, True), (0.1, 0.01, False), (0.5, 0.5, True), (0.1, 0.0, True)):
+        want, info_o = oracle.density_mask(xyz, voxel_size=vs, threshold_percentage=thr, keep_multicluster=multi)
+        got, info = density.density_filter(torch.from_numpy(xyz).to(cuda), vs, thr, keep_multicluster=multi)
+        assert info["clusters"] == info_o["clusters"], (vs, thr, multi)
+        assert np.array_equal(got.cpu().numpy(), want), (vs, thr, multi)
+
+
 def test_bbox_alpha_match_oracle(cuda, gsx_lib):
     import torch
     import oracle
