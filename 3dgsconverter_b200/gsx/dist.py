@@ -288,7 +288,7 @@ def build_grid_distributed(xyz_local: torch.Tensor, group=None, ops=None, stamps
     # 2. A: stable partition by bucket owner; the G x G count matrix gives every split and segment size
     pos4, cuts = ops.local_run(xyz_local, idx_base, n_global, world, bmin, cell)
     send = (cuts[1:] - cuts[:-1]).contiguous()
-    st.mark("build")
+    st.mark("build_A_partition")
     counts = torch.empty(world * world, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(counts, send, group=group)
     counts = counts.cpu().numpy().reshape(world, world)           # host sync 2: counts[r][o] = r sends to owner o
@@ -301,16 +301,16 @@ def build_grid_distributed(xyz_local: torch.Tensor, group=None, ops=None, stamps
     # 3. each point crosses NVLink once, to the owner of its bucket
     pos4_r = torch.empty((m, 4), dtype=torch.float32, device=dev)
     dist.all_to_all_single(pos4_r, pos4, recv_l, send_l, group=group)
-    st.mark("nccl")
+    st.mark("nccl_all_to_all")
     # 4. B: owner sort straight into the slot, then the ragged all-gather of the slots
     ws, spos_full = ops.new_grid_storage(n_global, dev)
     ops.merge_into(pos4_r, n_global, bmin, cell, spos_full[seg_base: seg_base + m])
-    st.mark("build")
+    st.mark("build_B_owner_sort")
     exchange_segments(spos_full, seg_sizes, rank, group)
-    st.mark("nccl")
+    st.mark("nccl_segments")
     # 5. C: table, boxes, bucket boxes -- replicated, two streaming passes over n_global
     grid = ops.finish(ws, spos_full, n_global, bmin, cell)
-    st.mark("build")
+    st.mark("build_C_table_boxes")
     return grid, sizes, seg_sizes
 
 
@@ -331,10 +331,10 @@ def sor_filter_distributed(xyz_local: torch.Tensor, k: int = 25, threshold_facto
         ops.mean_dists_range(grid, k, hash_mode, means_full, qb, qe)
     st.mark("knn")
     means_local = route_to_slabs(means_full, sizes, rank, group)
-    st.mark("nccl")
+    st.mark("nccl_route_means")
     meanstd = mean_std_distributed(means_local, sizes, rank, group, ops=ops)
     mask = ops.threshold(means_local, meanstd, threshold_factor)
-    st.mark("tail")
+    st.mark("stats_mask")
     if timings is not None:
         timings.update(st.result())
     return (mask, means_local) if return_means else mask
