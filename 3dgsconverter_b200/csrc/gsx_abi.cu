@@ -10,7 +10,9 @@
 #include "gsx_kmeans.cuh"
 #include "gsx_knn_exact.cuh"
 #include "gsx_masks.cuh"
+#include "gsx_morton.cuh"
 #include "gsx_radix.cuh"
+#include "gsx_records.cuh"
 #include "gsx_sog.cuh"
 #include "gsx_sor.cuh"
 
@@ -489,6 +491,40 @@ int gsx_kmeans_host_batched(const float* X_host, const int64_t* row_off_host, in
     GSX_CUDA_CHECK(cudaMemcpyAsync(labels_host, L.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     GSX_CUDA_CHECK(cudaStreamSynchronize(st));
     return GSX_OK;
+}
+
+/* ------------------------------------------------------------------ device-resident records (SURVEY 8f 2,4) */
+int gsx_records_extract_xyz_opacity(const float* rows_dev, int64_t n, int32_t F, int32_t cx, int32_t cy, int32_t cz,
+                                    int32_t cop, float* xyz_dev, float* opacity_dev, void* stream) {
+    return records_extract_xyz_opacity(rows_dev, n, F, cx, cy, cz, cop, xyz_dev, opacity_dev, (cudaStream_t)stream);
+}
+int gsx_records_gather_rows(const float* rows_dev, const int32_t* idx_dev, int64_t m, int32_t F, float* out_dev,
+                            void* stream) {
+    return records_gather_rows(rows_dev, idx_dev, m, F, out_dev, (cudaStream_t)stream);
+}
+int gsx_records_color_rgba8(const float* rows_dev, int64_t n, int32_t F, int32_t c0, int32_t c1, int32_t c2, int32_t cop,
+                            float scale, uint8_t* rgba_dev, void* stream) {
+    return records_color_rgba8(rows_dev, n, F, c0, c1, c2, cop, scale, rgba_dev, (cudaStream_t)stream);
+}
+int gsx_records_scale_exp(const float* rows_dev, int64_t n, int32_t F, int32_t s0, int32_t s1, int32_t s2, float* out_dev,
+                          void* stream) {
+    return records_scale_exp(rows_dev, n, F, s0, s1, s2, out_dev, (cudaStream_t)stream);
+}
+
+/* ------------------------------------------------------------------ Morton ordering primitive */
+int64_t gsx_morton_workspace_bytes(int64_t n) { return morton_workspace_bytes(n); }
+int gsx_morton_order(const float* xyz_dev, int64_t n, int32_t* order_dev, int32_t run_limit, int32_t* levels_out, void* ws,
+                     int64_t ws_bytes, void* stream) {
+    int lv = 0;
+    int rc = morton_order(xyz_dev, n, order_dev, run_limit, 16, &lv, ws, ws_bytes, (cudaStream_t)stream);
+    if (levels_out) *levels_out = lv;
+    return rc;
+}
+int gsx_chunk_minmax(const float* rows_dev, int64_t n, int32_t F, const int32_t* order_dev, int32_t chunk,
+                     const int32_t* cols_host, int32_t ncol, float clip_lo, float clip_hi, float* lo_dev, float* hi_dev,
+                     void* ws, int64_t ws_bytes, void* stream) {
+    return chunk_minmax(rows_dev, n, F, order_dev, chunk, cols_host, ncol, clip_lo, clip_hi, lo_dev, hi_dev, ws, ws_bytes,
+                        (cudaStream_t)stream);
 }
 
 /* free / total device memory of the current device (sizing decisions of the host-buffer entry points) */

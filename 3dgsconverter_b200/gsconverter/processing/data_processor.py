@@ -39,17 +39,26 @@ def _require_backend():
 
 class DataProcessor:
     defer_compaction = os.environ.get("GSX_DEFER_COMPACTION", "0") == "1"
+    # keep the WHOLE records (all 62 float32 fields) in HBM: one upload, survivors gathered on the
+    # device, one D2H when `.data` is read -- instead of fancy-indexing 248 bytes per splat on one CPU thread.
+    device_records = os.environ.get("GSX_DEVICE_RECORDS", "0") == "1"
 
     def __init__(self, data):
         self._data = data
         self._chain = None      # device-resident working set (gsx.pipeline.FilterChain)
         self._pending = False   # host records not yet gathered with the chain's surviving indices
+        self._records = None    # gsx.records.DeviceRecords (device_records mode)
 
     # ------------------------------------------------------------------ host records, lazily compacted
     @property
     def data(self):
         if self._pending:
-            self._data = self._data[self._chain.indices()]
+            if self._records is not None:
+                if self._chain.idx is not None:
+                    self._records = self._records.gather(self._chain.idx)
+                self._data = self._records.to_host()
+            else:
+                self._data = self._data[self._chain.indices()]
             self._chain.rebase()
             self._pending = False
         return self._data
@@ -58,18 +67,27 @@ class DataProcessor:
     def data(self, value):
         self._data = value
         self._chain = None
+        self._records = None
         self._pending = False
 
     def invalidate(self):
         """Drop the device-resident columns (call after editing coordinates / opacity of ``.data`` in place)."""
         _ = self.data          # gathers pending survivors first
         self._chain = None
+        self._records = None
 
     def _working_set(self):
         _require_backend()
         if self._chain is None:
             from gsx.pipeline import FilterChain
             v = self._data
+            if self.device_records:
+                from gsx import records
+                if records.is_packed_f32(v):
+                    self._records = records.DeviceRecords.from_structured(v)
+                    xyz, op = self._records.xyz_opacity()
+                    self._chain = FilterChain(xyz, op)
+                    return self._chain
             xyz = np.column_stack((v["x"], v["y"], v["z"]))
             op = v["opacity"] if "opacity" in v.dtype.names else None
             self._chain = FilterChain(xyz, op)

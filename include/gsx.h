@@ -233,6 +233,42 @@ int gsx_kmeans_tc_debug_scores(const float* X_dev, int64_t rows, const float* C_
 int gsx_kmeans_host(const float* X_host, int64_t n, int32_t K, int32_t D, int32_t max_iter, float* C_host_inout,
                     int32_t* labels_host, int32_t assign_mode);
 
+/* ---- device-resident splat records ------------------------------------------------
+ * rows_dev: the reference's interchange records (structures.py:23-59) as a row-major float32 matrix [n, F]
+ * (F = 62 for SH degree 3), uploaded once.  Column arguments are field positions inside a row.
+ *  extract : np.column_stack((x,y,z)) / v['opacity'] of data_processor.py:38,139,184 -> xyz [n,3], opacity [n] (or NULL)
+ *  gather  : vertices[mask] of data_processor.py:114,149,209,224 for the surviving (ascending) row indices
+ *  color   : RGBA8 of formats/splat.py:131-144, ksplat.py:464-468: clip((0.5 + scale*f_dc)*255).astype(u8) x3 (bit-exact
+ *            float32 ops; scale = SH_C0 for .splat/.ksplat, 0.15 for spz.py:131) and clip(sigmoid(opacity)*255).astype(u8)
+ *            (expf: may differ from NumPy's SIMD exp by one count on a ~1e-5 fraction of the splats)
+ *  scale   : np.exp(scale_0..2) of formats/splat.py:108, ksplat.py:447 -> float32 [n,3] */
+int gsx_records_extract_xyz_opacity(const float* rows_dev, int64_t n, int32_t F, int32_t cx, int32_t cy, int32_t cz,
+                                    int32_t cop, float* xyz_dev, float* opacity_dev, void* stream);
+int gsx_records_gather_rows(const float* rows_dev, const int32_t* idx_dev, int64_t m, int32_t F, float* out_dev,
+                            void* stream);
+int gsx_records_color_rgba8(const float* rows_dev, int64_t n, int32_t F, int32_t c0, int32_t c1, int32_t c2, int32_t cop,
+                            float scale, uint8_t* rgba_dev, void* stream);
+int gsx_records_scale_exp(const float* rows_dev, int64_t n, int32_t F, int32_t s0, int32_t s1, int32_t s2, float* out_dev,
+                          void* stream);
+
+/* ---- Morton ordering as a shared primitive ----------------------------------------------
+ * formats/compressed_ply.py:252-297 (_sort_morton_order): order_dev[j] = index of the j-th splat in the recursive
+ * 3 x 10-bit Morton order (codes relative to the bounding box of the group; every run of equal codes longer than
+ * run_limit (the reference: 256) is re-normalised to its own box and sorted again, until it is short or has no
+ * extent).  Equal codes inside a finished run come out in ascending original index (the reference's unstable
+ * np.argsort leaves that order unspecified).  *levels_out = number of levels that ran. */
+int64_t gsx_morton_workspace_bytes(int64_t n);
+int gsx_morton_order(const float* xyz_dev, int64_t n, int32_t* order_dev, int32_t run_limit, int32_t* levels_out, void* ws,
+                     int64_t ws_bytes, void* stream);
+/* compressed_ply.py:206-246 (per-256-splat chunk bounds) / ksplat.py:426-441 (np.minimum/maximum.reduceat per
+ * bucket): min and max of ncol (<= 8) columns cols_host[] of the row-major float32 matrix rows_dev [n,F] over
+ * consecutive chunks of `chunk` rows taken in the order order_dev (NULL = identity); values are clipped to
+ * [clip_lo, clip_hi] first (np.clip(scale, -20, 20) of compressed_ply.py:213-215; pass -inf/+inf for none).
+ * lo_dev / hi_dev: float32 [ceil(n/chunk), ncol].  ws >= 64 bytes. */
+int gsx_chunk_minmax(const float* rows_dev, int64_t n, int32_t F, const int32_t* order_dev, int32_t chunk,
+                     const int32_t* cols_host, int32_t ncol, float clip_lo, float clip_hi, float* lo_dev, float* hi_dev,
+                     void* ws, int64_t ws_bytes, void* stream);
+
 /* The SOG shN schedule (formats/sog.py:536-549: up to 64 chunks of one SH block, each clustered by its own
  * gpu_ops.kmeans call) in ONE call on HOST buffers: one upload of the block, one batched launch per phase.
  * nprob problems back to back in X_host (rows row_off[p] .. row_off[p+1]), K centroids each;
