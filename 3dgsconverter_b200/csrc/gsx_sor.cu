@@ -604,6 +604,21 @@ struct TopK {
     }
 };
 
+// positions in the hash-sorted order fit 31 bits (n < 2^31 - 64): 32-bit index arithmetic in the scan loops
+#ifndef GSX_KNN_I32
+#define GSX_KNN_I32 1
+#endif
+#if GSX_KNN_I32
+typedef int pos_t;
+#else
+typedef int64_t pos_t;
+#endif
+// A/B variant named by BASELINE.json's north_star: stage the query's centre bucket (<= 64 points = 1 KiB) into shared
+// memory with a 1-D TMA bulk copy (cp.async.bulk + mbarrier) once per cell change, and scan it from there.
+#ifndef GSX_KNN_TMA
+#define GSX_KNN_TMA 0
+#endif
+
 #ifndef GSX_MERGE_THRESHOLD
 #define GSX_MERGE_THRESHOLD 9
 #endif
@@ -611,11 +626,12 @@ constexpr int kMergeThreshold = GSX_MERGE_THRESHOLD;  // serial insert ~11 instr
 
 // distance of the query to candidate j and ballot/shfl insertion of the lanes that beat tau
 template <int NREG, bool STATS>
-__device__ __forceinline__ void scan32(const float4* __restrict__ spos, int64_t j, bool valid, float qx, float qy,
-                                       float qz, TopK<NREG>& tk, int lane, unsigned long long& n_scanned) {
+__device__ __forceinline__ void scan32(const float4* __restrict__ spos, pos_t j, bool valid, float qx, float qy,
+                                       float qz, TopK<NREG>& tk, int lane, unsigned long long& n_scanned,
+                                       const float4* sbuf = nullptr) {
     float d2 = INFINITY;
     if (valid) {
-        float4 c = __ldg(spos + j);
+        float4 c = sbuf ? sbuf[lane] : __ldg(spos + j);
         float ax = __fsub_rn(qx, c.x), ay = __fsub_rn(qy, c.y), az = __fsub_rn(qz, c.z);
         d2 = __fadd_rn(__fadd_rn(__fmul_rn(ax, ax), __fmul_rn(ay, ay)), __fmul_rn(az, az));
     }
@@ -646,6 +662,16 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
               uint32_t n, uint64_t M, unsigned long long* __restrict__ stats) {
     const int lane = lane_id();
     unsigned long long st_visits = 0, st_scanned = 0, st_boxes = 0, st_queries = 0;
+#if GSX_KNN_TMA
+    __shared__ __align__(128) float4 s_stage[8][kSmallBucket];
+    __shared__ __align__(8) unsigned long long s_bar[8];
+    float4* wbuf = s_stage[threadIdx.x >> 5];
+    const uint32_t bar_addr = (uint32_t)__cvta_generic_to_shared(&s_bar[threadIdx.x >> 5]);
+    uint32_t bar_phase = 0;
+    int staged_s = -1, staged_c = 0;
+    if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_addr) : "memory");
+    __syncwarp();
+#endif
     // probe offsets of lane p<27 in the reference's loop order (dx outer, dz inner)
     const int pdx = lane / 9 - 1, pdy = (lane / 3) % 3 - 1, pdz = lane % 3 - 1;
 
@@ -684,6 +710,38 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
                         blx = b0.x, bly = b0.y, blz = b0.z, bhx = b1.x, bhy = b1.y, bhz = b1.z;
                     }
                 }
+#if GSX_KNN_TMA
+                {   // stage the centre bucket of the new cell (if it is a small one) for the queries that share it
+                    const int s13 = __shfl_sync(GSX_FULL, ps, 13), c13 = __shfl_sync(GSX_FULL, pc, 13);
+                    staged_c = 0;
+                    if (c13 > 0 && c13 <= kSmallBucket) {
+                        __syncwarp();   // every lane is done with the previous contents of wbuf
+                        if (lane == 0) {
+                            const uint32_t bytes = (uint32_t)c13 * 16u;
+                            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_addr), "r"(bytes) : "memory");
+                            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                             (uint32_t)__cvta_generic_to_shared(wbuf)),
+                                         "l"(spos + s13), "r"(bytes), "r"(bar_addr)
+                                         : "memory");
+                        }
+                        uint32_t ok = 0;
+                        for (unsigned spin = 0; !ok && spin < (1u << 24); ++spin) {   // bounded: never hang the GPU
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\t"
+                                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                                "selp.u32 %0, 1, 0, p;\n\t}"
+                                : "=r"(ok)
+                                : "r"(bar_addr), "r"(bar_phase)
+                                : "memory");
+                        }
+                        bar_phase ^= 1u;
+                        if (__all_sync(GSX_FULL, ok != 0)) {
+                            staged_s = s13;
+                            staged_c = c13;
+                        }
+                    }
+                }
+#endif
             }
             if (STATS) {
                 int tot = pc;
@@ -714,8 +772,8 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
                 int s13 = __shfl_sync(GSX_FULL, ps, 13), c13 = __shfl_sync(GSX_FULL, pc, 13);
                 if (c13 > kSmallBucket && i >= s13 && i < (int64_t)s13 + c13) {
                     skip_chunk = (int)(i >> 5);
-                    int64_t j = ((int64_t)skip_chunk << 5) + lane;
-                    scan32<NREG, STATS>(spos, j, j >= s13 && j < (int64_t)s13 + c13, q.x, q.y, q.z, tk, lane,
+                    const pos_t j = ((pos_t)skip_chunk << 5) + lane;
+                    scan32<NREG, STATS>(spos, j, j >= s13 && j < (pos_t)s13 + c13, q.x, q.y, q.z, tk, lane,
                                         st_scanned);
                 }
             }
@@ -727,11 +785,19 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
                 const int p = __ffs(__ballot_sync(GSX_FULL, pkey == mp)) - 1;
                 if (lane == p) pkey = 0xffffffffu;
                 const int s = __shfl_sync(GSX_FULL, ps, p), c = __shfl_sync(GSX_FULL, pc, p);
-                const int64_t e = (int64_t)s + c;
+                const pos_t e = (pos_t)s + c;
                 if (c <= kSmallBucket) {
+#if GSX_KNN_TMA
+                    const bool from_smem = staged_c > 0 && s == staged_s;   // warp-uniform
 #pragma unroll 1
-                    for (int64_t base = s; base < e; base += 32)
+                    for (pos_t base = s; base < e; base += 32)
+                        scan32<NREG, STATS>(spos, base + lane, base + lane < e, q.x, q.y, q.z, tk, lane, st_scanned,
+                                            from_smem ? wbuf + (base - s) : nullptr);
+#else
+#pragma unroll 1
+                    for (pos_t base = s; base < e; base += 32)
                         scan32<NREG, STATS>(spos, base + lane, base + lane < e, q.x, q.y, q.z, tk, lane, st_scanned);
+#endif
                     continue;
                 }
                 const int skip = p == 13 ? skip_chunk : -1;
@@ -764,7 +830,7 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
                             if (mc == 0xffffffffu || !(__uint_as_float(mc) < tk.tau)) break;
                             int srcc = __ffs(__ballot_sync(GSX_FULL, ckey == mc)) - 1;
                             if (lane == srcc) ckey = 0xffffffffu;
-                            int64_t j = ((int64_t)(sup * 32 + srcc) << 5) + lane;
+                            const pos_t j = ((pos_t)(sup * 32 + srcc) << 5) + lane;
                             scan32<NREG, STATS>(spos, j, j >= s && j < e, q.x, q.y, q.z, tk, lane, st_scanned);
                         }
                     }
