@@ -7,6 +7,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <nvtx3/nvToolsExt.h>   // header-only (dlopen of the injection library at run time; no link dependency)
 
 #define GSX_OK 0
 #define GSX_ERR_CUDA -1
@@ -42,6 +43,13 @@ void count_launch();
             return (code);             \
         }                              \
     } while (0)
+
+// NVTX range of a host-side stage (visible in nsys / ncu --nvtx): one per C-ABI stage, RAII
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+#define GSX_NVTX(name) gsx::NvtxRange _gsx_nvtx_range(name)
 
 // Device properties cached per process (queried on first use for the current device).
 int sm_count();

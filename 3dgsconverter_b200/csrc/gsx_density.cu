@@ -272,6 +272,7 @@ __global__ void k_vox_dense_counts_hash_wide(const long long* __restrict__ dense
 int density_voxel_count(const float* xyz, int64_t n, float voxel, int64_t min_points, int64_t* dense_vox_host,
                         int32_t* dense_cnt_host, int64_t cap, int64_t* n_dense_host, int64_t* n_voxels_host, void* ws,
                         int64_t ws_bytes, cudaStream_t st) {
+    GSX_NVTX("gsx::density_voxel_count");
     GSX_REQUIRE(n >= 1, GSX_ERR_ARG, "density: n must be >= 1");
     GSX_REQUIRE(voxel > 0.f, GSX_ERR_ARG, "density: voxel size must be > 0");
     GSX_REQUIRE(ws_bytes >= density_workspace_bytes(n, cap), GSX_ERR_WORKSPACE, "density: workspace too small");
@@ -530,6 +531,7 @@ __global__ void __launch_bounds__(256) k_vox_member4(const float4* __restrict__ 
 
 int density_member_mask(const float* xyz, int64_t n, float voxel, const int64_t* keep, int64_t n_keep, uint8_t* mask,
                         void* ws, int64_t ws_bytes, cudaStream_t st) {
+    GSX_NVTX("gsx::density_member_mask");
     if (n == 0) return GSX_OK;
     GSX_REQUIRE(voxel > 0.f, GSX_ERR_ARG, "density: voxel size must be > 0");
     if (n_keep == 0) {

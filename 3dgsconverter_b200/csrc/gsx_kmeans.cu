@@ -659,6 +659,7 @@ static int points_per_thread(int D) {
 int kmeans_lloyd(const float* X, const int64_t* row_off, int nprob, int K, int D, int max_iter, float* C, int* labels,
                  int* counts, void* ws, int64_t ws_bytes, int assign_mode, unsigned long long* tc_stats,
                  cudaStream_t st) {
+    GSX_NVTX("gsx::kmeans_lloyd");
     GSX_REQUIRE(assign_mode >= 0 && assign_mode <= 3, GSX_ERR_ARG, "kmeans: bad assign_mode %d", assign_mode);
     if (assign_mode == GSX_KM_ASSIGN_TENSOR)
         GSX_REQUIRE(kmeans_tc_supported(K, D), GSX_ERR_UNSUPPORTED,

@@ -183,6 +183,7 @@ int64_t morton_workspace_bytes(int64_t n) {
 
 int morton_order(const float* xyz, int64_t n, int32_t* order, int limit, int max_levels, int* levels_out, void* ws,
                  int64_t ws_bytes, cudaStream_t st) {
+    GSX_NVTX("gsx::morton_order");
     GSX_REQUIRE(n >= 0 && n < 2147483584ll, GSX_ERR_ARG, "morton: n out of range");
     if (levels_out) *levels_out = 0;
     if (n == 0) return GSX_OK;

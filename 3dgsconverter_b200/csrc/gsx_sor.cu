@@ -388,6 +388,7 @@ static int sor_finish(const float* xyz, int64_t n, const float* bmin, float cell
 }
 
 int sor_build(const float* xyz, int64_t n, const float* bmin, float cell, SorWs& w, cudaStream_t st) {
+    GSX_NVTX("gsx::sor_build");
     int blocks = (int)((n + 255) / 256);
     k_sor_keys<<<blocks, 256, 0, st>>>(xyz, n, bmin[0], bmin[1], bmin[2], cell, 0xFFFFFFFFFFFFFFFFull / (uint64_t)n,
                                        w.keys0, w.vals0);
@@ -454,6 +455,7 @@ static int hash_bits_of(int64_t n) {
 int sor_dist_local_run(const float* xyz, int64_t n_local, int64_t idx_base, int64_t n_global, int world,
                        const float* bmin, float cell, float4* pos4_out, long long* cuts_dev, SorWs& w,
                        cudaStream_t st) {
+    GSX_NVTX("gsx::sor_dist_local_run");
     GSX_REQUIRE(world >= 1 && world <= 255, GSX_ERR_ARG, "sor: world size must be in [1,255]");
     if (n_local == 0) {
         GSX_CUDA_CHECK(cudaMemsetAsync(cuts_dev, 0, (size_t)(world + 1) * sizeof(long long), st));
@@ -494,6 +496,7 @@ __global__ void __launch_bounds__(256) k_sor_keys_pos4(const float4* __restrict_
 
 int sor_dist_merge(const float4* pos4_in, int64_t m, int64_t n_global, const float* bmin, float cell, float4* pos4_out,
                    SorWs& w, cudaStream_t st) {
+    GSX_NVTX("gsx::sor_dist_merge");
     if (m == 0) return GSX_OK;
     int blocks = (int)((m + 255) / 256);
     k_sor_keys_pos4<<<blocks, 256, 0, st>>>(pos4_in, m, n_global, bmin[0], bmin[1], bmin[2], cell,
@@ -511,6 +514,7 @@ int sor_dist_merge(const float4* pos4_in, int64_t m, int64_t n_global, const flo
 
 // stage C: everything gsx_sor_build produces, from an already hash-sorted float4 array
 int sor_build_from_sorted(const float4* spos_in, int64_t n, const float* bmin, float cell, SorWs& w, cudaStream_t st) {
+    GSX_NVTX("gsx::sor_build_from_sorted");
     if (spos_in != w.spos)
         GSX_CUDA_CHECK(cudaMemcpyAsync(w.spos, spos_in, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, st));
     w.keys_sorted = nullptr;
@@ -879,6 +883,7 @@ static int launch_knn(SorWs& w, int64_t q_begin, int64_t q_end, int K, int hash_
 
 int sor_mean_dists(SorWs& w, int64_t q_begin, int64_t q_end, int k, int hash_mode, const float* bmin, float cell,
                    float* final_means, unsigned long long* stats, cudaStream_t st) {
+    GSX_NVTX("gsx::sor_mean_dists(k_sor_knn)");
     int64_t n = w.n;
     GSX_REQUIRE(k >= 1, GSX_ERR_ARG, "sor: k must be >= 1 (got %d)", k);
     GSX_REQUIRE(hash_mode == 0 || hash_mode == 1, GSX_ERR_ARG, "sor: bad hash_mode %d", hash_mode);

@@ -152,6 +152,7 @@ static int pairwise_pass(const float* a, int64_t n, int dmax, float* slot, float
 }
 
 int mean_std_f32(const float* a, int64_t n, float* out_dev, void* ws, size_t ws_bytes, cudaStream_t st) {
+    GSX_NVTX("gsx::mean_std_f32");
     GSX_REQUIRE(n >= 1, GSX_ERR_ARG, "mean_std: n must be >= 1");
     GSX_REQUIRE(ws_bytes >= mean_std_ws_bytes(n), GSX_ERR_WORKSPACE, "mean_std: workspace too small");
     int dmax = pairwise_depth(n);

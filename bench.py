@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the gsx hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl gsx|reference] [--config c2|c3|c4|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl gsx|reference] [--config c2|c3|c4|c5] [--splats-per-gpu N]
     torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 Default (`--config c2`, the driver's contract line).  Metric: Msplats/s of Statistical Outlier Removal, k=16,
@@ -55,7 +55,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gsx", choices=["gsx", "reference"])
     ap.add_argument("--config", default="c2", choices=["c2", "c3", "c4", "c5"])
-    ap.add_argument("--n", type=int, default=None, help="splats per GPU (default: the config's)")
+    ap.add_argument("--splats-per-gpu", "--points", dest="n", type=int, default=None,
+                    help="splats per GPU (default: the config's); not `--n`: torchrun would swallow it")
     ap.add_argument("--kind", default="mixed", choices=["mixed", "uniform", "clustered"])
     ap.add_argument("--hash", default="i32wrap", choices=["i32wrap", "i64"])
     ap.add_argument("--cpu-sample", type=int, default=1_000_000, help="points of the in-line CPU-baseline sample")
