@@ -660,11 +660,13 @@ int kmeans_lloyd(const float* X, const int64_t* row_off, int nprob, int K, int D
                  int* counts, void* ws, int64_t ws_bytes, int assign_mode, unsigned long long* tc_stats,
                  cudaStream_t st) {
     GSX_NVTX("gsx::kmeans_lloyd");
-    GSX_REQUIRE(assign_mode >= 0 && assign_mode <= 3, GSX_ERR_ARG, "kmeans: bad assign_mode %d", assign_mode);
-    if (assign_mode == GSX_KM_ASSIGN_TENSOR)
+    GSX_REQUIRE(assign_mode >= 0 && assign_mode <= 4, GSX_ERR_ARG, "kmeans: bad assign_mode %d", assign_mode);
+    if (assign_mode == GSX_KM_ASSIGN_TENSOR || assign_mode == GSX_KM_ASSIGN_TENSOR_TF32)
         GSX_REQUIRE(kmeans_tc_supported(K, D), GSX_ERR_UNSUPPORTED,
                     "kmeans: tensor-core assign needs D in {9,24,45} and K <= 256 (got K=%d D=%d)", K, D);
-    const bool use_tc = assign_mode == GSX_KM_ASSIGN_TENSOR || (assign_mode == GSX_KM_ASSIGN_AUTO && kmeans_tc_supported(K, D));
+    const bool use_tc = assign_mode == GSX_KM_ASSIGN_TENSOR || assign_mode == GSX_KM_ASSIGN_TENSOR_TF32 ||
+                        (assign_mode == GSX_KM_ASSIGN_AUTO && kmeans_tc_supported(K, D));
+    const int tc_variant = assign_mode == GSX_KM_ASSIGN_TENSOR_TF32 ? 0 : 2;
     const bool prefilter = assign_mode == GSX_KM_ASSIGN_FMA_PREFILTER;
     GSX_REQUIRE(nprob >= 1 && K >= 1 && D >= 1 && max_iter >= 0, GSX_ERR_ARG, "kmeans: bad shape");
     const int64_t n_total = row_off[nprob] - row_off[0];
@@ -705,7 +707,7 @@ int kmeans_lloyd(const float* X, const int64_t* row_off, int nprob, int K, int D
     if (use_tc) GSX_CUDA_CHECK(cudaMemsetAsync(w.err, 0, sizeof(int), st));
     for (int it = 0; it < max_iter; ++it) {
         if (use_tc) {
-            int rc = kmeans_assign_tc(X, (long long)n_total * D, C, labels, dp, nprob, K, D, tc_tiles, 0, 0, nullptr,
+            int rc = kmeans_assign_tc(X, (long long)n_total * D, C, labels, dp, nprob, K, D, tc_tiles, tc_variant, 0, nullptr,
                                       tc_stats, w.err, st);
             if (rc) return rc;
         } else

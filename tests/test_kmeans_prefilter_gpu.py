@@ -6,7 +6,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["fma", "tensor"])
+@pytest.fixture(params=["fma", "tensor", "tensor_tf32"])
 def mode(request, gsx_lib):
     return request.param
 
@@ -18,7 +18,7 @@ def _check(X, k, it, cuda, mode, seed=1234):
     np.random.seed(seed)
     init = oracle.kmeans_reference_init(X, k)
     Co, Lo, cnto = oracle.kmeans_lloyd(X, k, it, init=init)
-    if mode == "tensor" and not gk.tensor_core_supported(k, X.shape[1]):
+    if mode.startswith("tensor") and not gk.tensor_core_supported(k, X.shape[1]):
         pytest.skip("shape not supported by the tensor-core path")
     C, L, cnt = gk.kmeans_lloyd(torch.from_numpy(X).to(cuda), k, it, torch.from_numpy(init).to(cuda), assign=mode)
     assert np.array_equal(L.cpu().numpy(), Lo)
