@@ -265,10 +265,16 @@ __global__ void __launch_bounds__(1024)
         lo[1] = hi[1] = y;
         lo[2] = hi[2] = z;
     }
-    uint32_t hprev = __shfl_up_sync(GSX_FULL, h, 1), hnext = __shfl_down_sync(GSX_FULL, h, 1);
+    // neighbouring hashes: through shared memory inside the block (invalid threads hold the sentinel 0xffffffff, which
+    // no real bucket has: h < n < 2^31); only the two block-edge threads look at global memory
+    __shared__ uint32_t sh_h[1024];
+    sh_h[threadIdx.x] = h;
+    __syncthreads();
+    uint32_t hprev = threadIdx.x > 0 ? sh_h[threadIdx.x - 1] : 0xffffffffu;
+    uint32_t hnext = threadIdx.x < 1023 ? sh_h[threadIdx.x + 1] : 0xffffffffu;
     if (j < n) {
-        if (lane == 0) hprev = j > 0 ? hash_at(j - 1) : ~h;
-        if (lane == 31) hnext = j + 1 < n ? hash_at(j + 1) : ~h;
+        if (threadIdx.x == 0 && j > 0) hprev = hash_at(j - 1);
+        if (threadIdx.x == 1023 && j + 1 < n) hnext = hash_at(j + 1);
     }
     const bool start = j < n && (j == 0 || h != hprev);
     const bool end = j < n && (j == n - 1 || h != hnext);

@@ -904,17 +904,23 @@ def run_big(args):
               "sharding": "chunks are independent problems: no collective (SURVEY 8e)"}
         ms_total = ms_chain + ms_km
         # K-Means parity: rank 1's first chunk recomputed on rank 0 (same kernels, other GPU): bit-identical
-        if world > 1:
+        if world > 1:   # (the chunk length differs per rank: ship it first)
             blk = Xk[:rows].contiguous()
             ini = initk[0].contiguous()
             C1, _, _ = gk.kmeans_lloyd_batched(blk, [0, rows], 256, 10, ini.reshape(1, 256, -1))
             if rank == 1:
+                dist.send(torch.tensor([rows], dtype=torch.int64, device=dev), dst=0)
                 dist.send(blk, dst=0); dist.send(ini, dst=0); dist.send(C1.contiguous(), dst=0)
             if rank == 0:
-                rb, ri, rc = torch.empty_like(blk), torch.empty_like(ini), torch.empty_like(C1)
+                r1 = torch.zeros(1, dtype=torch.int64, device=dev)
+                dist.recv(r1, src=1)
+                r1 = int(r1.item())
+                rb = torch.empty((r1, blk.shape[1]), dtype=torch.float32, device=dev)
+                ri, rc = torch.empty_like(ini), torch.empty_like(C1)
                 dist.recv(rb, src=1); dist.recv(ri, src=1); dist.recv(rc, src=1)
-                C0, _, _ = gk.kmeans_lloyd_batched(rb, [0, rows], 256, 10, ri.reshape(1, 256, -1))
+                C0, _, _ = gk.kmeans_lloyd_batched(rb, [0, r1], 256, 10, ri.reshape(1, 256, -1))
                 km["parity_rank1_chunk_on_rank0"] = {"equal": bool(torch.equal(C0.view(torch.int32), rc.view(torch.int32))),
+                                                    "rows": r1,
                                                     "max_rel_err": float(((C0 - rc).abs() / rc.abs().clamp_min(1e-30)).max().item())}
         del Xk, initk
         torch.cuda.empty_cache()
