@@ -234,6 +234,15 @@ __global__ void __launch_bounds__(256) k_sor_keys(const float* __restrict__ xyz,
 // bucket is re-hashed from the position.  Outputs: {start,end} of every occupied bucket (tab_se pre-zeroed:
 // start == end == 0 <=> the reference's cell_start == -1), one bit per sorted position that starts a bucket,
 // and the bounding boxes of every chunk and super.
+// order-preserving float <-> uint32 (for redux.sync min/max); +/-inf map to the extremes, -0 < +0
+__device__ __forceinline__ uint32_t float_to_ord(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord_to_float(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+
 template <bool GATHER>
 __global__ void __launch_bounds__(1024)
     k_sor_finish(const float* __restrict__ xyz, const int32_t* __restrict__ order, const uint64_t* __restrict__ keys,
@@ -281,13 +290,12 @@ __global__ void __launch_bounds__(1024)
     if (start) tab_se[h].x = (int)j;
     if (end) tab_se[h].y = (int)(j + 1);
     const unsigned sb = __ballot_sync(GSX_FULL, start);
+    // chunk boxes: one redux.sync per component on order-preserving integer keys (exact: min/max only select)
 #pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lo[a] = fminf(lo[a], __shfl_xor_sync(GSX_FULL, lo[a], o));
-            hi[a] = fmaxf(hi[a], __shfl_xor_sync(GSX_FULL, hi[a], o));
-        }
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = ord_to_float(__reduce_min_sync(GSX_FULL, float_to_ord(lo[a])));
+        hi[a] = ord_to_float(__reduce_max_sync(GSX_FULL, float_to_ord(hi[a])));
+    }
     __shared__ float sm[6][32];
     const int w = threadIdx.x >> 5;
     const int64_t chunk = (int64_t)blockIdx.x * 32 + w;
@@ -334,13 +342,20 @@ __global__ void __launch_bounds__(256)
     const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (chunk * 32 >= n) return;
     unsigned m = startbits[chunk];
+    // the hash and the end of every bucket that starts in this chunk: one lane per start, in parallel
+    uint32_t my_h = 0;
+    int my_end = 0;
+    if ((m >> lane) & 1u) {
+        const float4 p0 = spos[chunk * 32 + lane];
+        my_h = bucket_of(p0.x, p0.y, p0.z, bx, by, bz, cell, n, M64);
+        my_end = tab_se[my_h].y;
+    }
     while (m) {
         const int src = __ffs(m) - 1;
         m &= m - 1;
         const int64_t s = chunk * 32 + src;
-        const float4 p0 = spos[s];
-        const uint32_t hb = bucket_of(p0.x, p0.y, p0.z, bx, by, bz, cell, n, M64);
-        const int64_t end = tab_se[hb].y;
+        const uint32_t hb = __shfl_sync(GSX_FULL, my_h, src);
+        const int64_t end = __shfl_sync(GSX_FULL, my_end, src);
         float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
         int64_t cf = (s + 31) >> 5, cl = end >> 5;  // full chunks [cf, cl)
         int64_t head_end = cf * 32, tail_begin = cl * 32;
