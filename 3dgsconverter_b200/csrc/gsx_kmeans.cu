@@ -661,12 +661,12 @@ int kmeans_lloyd(const float* X, const int64_t* row_off, int nprob, int K, int D
                  cudaStream_t st) {
     GSX_NVTX("gsx::kmeans_lloyd");
     GSX_REQUIRE(assign_mode >= 0 && assign_mode <= 4, GSX_ERR_ARG, "kmeans: bad assign_mode %d", assign_mode);
-    if (assign_mode == GSX_KM_ASSIGN_TENSOR || assign_mode == GSX_KM_ASSIGN_TENSOR_TF32)
+    if (assign_mode == GSX_KM_ASSIGN_TENSOR || assign_mode == GSX_KM_ASSIGN_TENSOR_BF16)
         GSX_REQUIRE(kmeans_tc_supported(K, D), GSX_ERR_UNSUPPORTED,
                     "kmeans: tensor-core assign needs D in {9,24,45} and K <= 256 (got K=%d D=%d)", K, D);
-    const bool use_tc = assign_mode == GSX_KM_ASSIGN_TENSOR || assign_mode == GSX_KM_ASSIGN_TENSOR_TF32 ||
+    const bool use_tc = assign_mode == GSX_KM_ASSIGN_TENSOR || assign_mode == GSX_KM_ASSIGN_TENSOR_BF16 ||
                         (assign_mode == GSX_KM_ASSIGN_AUTO && kmeans_tc_supported(K, D));
-    const int tc_variant = assign_mode == GSX_KM_ASSIGN_TENSOR_TF32 ? 0 : 2;
+    const int tc_variant = assign_mode == GSX_KM_ASSIGN_TENSOR_BF16 ? 2 : 0;   // TF32 is the measured-faster default
     const bool prefilter = assign_mode == GSX_KM_ASSIGN_FMA_PREFILTER;
     GSX_REQUIRE(nprob >= 1 && K >= 1 && D >= 1 && max_iter >= 0, GSX_ERR_ARG, "kmeans: bad shape");
     const int64_t n_total = row_off[nprob] - row_off[0];

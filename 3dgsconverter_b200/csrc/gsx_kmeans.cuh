@@ -5,7 +5,7 @@
 #define GSX_KM_ASSIGN_STRICT 1
 #define GSX_KM_ASSIGN_FMA_PREFILTER 2
 #define GSX_KM_ASSIGN_TENSOR 3
-#define GSX_KM_ASSIGN_TENSOR_TF32 4
+#define GSX_KM_ASSIGN_TENSOR_BF16 4
 
 namespace gsx {
 

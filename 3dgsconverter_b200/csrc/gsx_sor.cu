@@ -68,6 +68,7 @@ SorWs sor_carve(void* ws, int64_t ws_bytes, int64_t n, size_t sort_ws_bytes) {
     w.tab_se = c.take<int2>(n);
     w.tab_box = c.take<float4>(2 * n);
     w.startbits = c.take<uint32_t>(nchunk);
+    w.cellbits = c.take<uint32_t>(nchunk);
     w.caabb = c.take<float4>(2 * nchunk);
     w.saabb = c.take<float4>(2 * nsuper);
     w.partial = c.take<float>(6 * 1024);
@@ -247,8 +248,8 @@ template <bool GATHER>
 __global__ void __launch_bounds__(1024)
     k_sor_finish(const float* __restrict__ xyz, const int32_t* __restrict__ order, const uint64_t* __restrict__ keys,
                  float4* __restrict__ spos, int64_t n, float bx, float by, float bz, float cell, uint64_t M64,
-                 int2* __restrict__ tab_se, uint32_t* __restrict__ startbits, float4* __restrict__ caabb,
-                 float4* __restrict__ saabb) {
+                 int2* __restrict__ tab_se, uint32_t* __restrict__ startbits, uint32_t* __restrict__ cellbits,
+                 float4* __restrict__ caabb, float4* __restrict__ saabb) {
     const int64_t j = (int64_t)blockIdx.x * 1024 + threadIdx.x;
     const int lane = lane_id();
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -258,6 +259,7 @@ __global__ void __launch_bounds__(1024)
         const float4 q = spos[t];
         return bucket_of(q.x, q.y, q.z, bx, by, bz, cell, n, M64);
     };
+    int gcx = 0x7fffffff, gcy = 0, gcz = 0;   // grid cell of this position (gpu_ops.py:113-115 arithmetic)
     if (j < n) {
         float x, y, z;
         if (GATHER) {
@@ -270,6 +272,9 @@ __global__ void __launch_bounds__(1024)
             x = p.x, y = p.y, z = p.z;
             h = bucket_of(x, y, z, bx, by, bz, cell, n, M64);
         }
+        gcx = (int)floorf(__fdiv_rn(__fsub_rn(x, bx), cell));
+        gcy = (int)floorf(__fdiv_rn(__fsub_rn(y, by), cell));
+        gcz = (int)floorf(__fdiv_rn(__fsub_rn(z, bz), cell));
         lo[0] = hi[0] = x;
         lo[1] = hi[1] = y;
         lo[2] = hi[2] = z;
@@ -285,6 +290,14 @@ __global__ void __launch_bounds__(1024)
         if (threadIdx.x == 0 && j > 0) hprev = hash_at(j - 1);
         if (threadIdx.x == 1023 && j + 1 < n) hnext = hash_at(j + 1);
     }
+    // "the query at this sorted position has another grid cell than the one before it": lets k_sor_knn skip the three
+    // divisions + vote per query.  Exact compare of the three cell indices (block edges are conservatively "new").
+    __shared__ int sh_c[3][1024];
+    sh_c[0][threadIdx.x] = gcx, sh_c[1][threadIdx.x] = gcy, sh_c[2][threadIdx.x] = gcz;
+    __syncthreads();
+    const bool newcell = j < n && (threadIdx.x == 0 || sh_c[0][threadIdx.x - 1] != gcx ||
+                                   sh_c[1][threadIdx.x - 1] != gcy || sh_c[2][threadIdx.x - 1] != gcz);
+    const unsigned cb = __ballot_sync(GSX_FULL, newcell);
     const bool start = j < n && (j == 0 || h != hprev);
     const bool end = j < n && (j == n - 1 || h != hnext);
     if (start) tab_se[h].x = (int)j;
@@ -302,6 +315,7 @@ __global__ void __launch_bounds__(1024)
     if (lane == 0) {
         if (chunk * 32 < n) {
             startbits[chunk] = sb;
+            cellbits[chunk] = cb;
             caabb[2 * chunk] = make_float4(lo[0], lo[1], lo[2], hi[0]);
             caabb[2 * chunk + 1] = make_float4(hi[1], hi[2], 0.f, 0.f);
         }
@@ -400,7 +414,7 @@ static int sor_finish(const float* xyz, int64_t n, const float* bmin, float cell
     GSX_CUDA_CHECK(cudaMemsetAsync(w.tab_se, 0, (size_t)n * sizeof(int2), st));
     k_sor_finish<GATHER><<<(int)((n + 1023) / 1024), 1024, 0, st>>>(xyz, w.order, w.keys_sorted, w.spos, n, bmin[0],
                                                                     bmin[1], bmin[2], cell, M64, w.tab_se, w.startbits,
-                                                                    w.caabb, w.saabb);
+                                                                    w.cellbits, w.caabb, w.saabb);
     GSX_KERNEL_CHECK();
     k_sor_bucket_boxes<<<(int)((n + 255) / 256), 256, 0, st>>>(w.startbits, w.spos, w.caabb, w.tab_se, n, bmin[0],
                                                                bmin[1], bmin[2], cell, M64, w.tab_box);
@@ -681,7 +695,7 @@ __device__ __forceinline__ void scan32(const float4* __restrict__ spos, pos_t j,
 template <int NREG, bool STATS>
 __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
     k_sor_knn(const float4* __restrict__ spos, const int2* __restrict__ tab_se, const float4* __restrict__ tab_box,
-              const float4* __restrict__ caabb,
+              const uint32_t* __restrict__ cellbits, const float4* __restrict__ caabb,
               const float4* __restrict__ saabb, float* __restrict__ final_means, unsigned int* __restrict__ work,
               int64_t q_begin, int64_t q_end, int K, int hash_mode, float bx, float by, float bz, float cell,
               uint32_t n, uint64_t M, unsigned long long* __restrict__ stats) {
@@ -709,12 +723,28 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
         int64_t qe = qb + kQueryBatch < q_end ? qb + kQueryBatch : q_end;
         // the 27 probes of a query depend only on its cell: consecutive hash-sorted queries mostly share
         // it, so the hashes and table entries are recomputed only when the cell changes
+#ifndef GSX_KNN_CELLBITS
+#define GSX_KNN_CELLBITS 1
+#endif
+#if GSX_KNN_CELLBITS
+        // one bit per sorted position (k_sor_finish): "another grid cell than the position before".  A batch is 16
+        // consecutive positions inside one 32-bit word (kQueryBatch divides 32, batches are aligned to q_begin).
+        const uint32_t cellword = __ldg(cellbits + (qb >> 5));
+#else
         int cgx = 0x7fffffff, cgy = 0, cgz = 0;
+#endif
         int ps = 0, pc = 0;                                  // lane p: bucket range of probe p
         float blx = 0.f, bly = 0.f, blz = 0.f, bhx = 0.f, bhy = 0.f, bhz = 0.f;  // and its bounding box
 #pragma unroll 1
         for (int64_t i = qb; i < qe; ++i) {
             const float4 q = __ldg(spos + i);
+#if GSX_KNN_CELLBITS
+            const uint32_t w_i = (i >> 5) == (qb >> 5) ? cellword : __ldg(cellbits + (i >> 5));
+            if (i == qb || ((w_i >> (i & 31)) & 1u)) {   // warp-uniform by construction
+                const int gx = (int)floorf(__fdiv_rn(__fsub_rn(q.x, bx), cell));
+                const int gy = (int)floorf(__fdiv_rn(__fsub_rn(q.y, by), cell));
+                const int gz = (int)floorf(__fdiv_rn(__fsub_rn(q.z, bz), cell));
+#else
             const int gx = (int)floorf(__fdiv_rn(__fsub_rn(q.x, bx), cell));
             const int gy = (int)floorf(__fdiv_rn(__fsub_rn(q.y, by), cell));
             const int gz = (int)floorf(__fdiv_rn(__fsub_rn(q.z, bz), cell));
@@ -724,6 +754,7 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
             // (vote makes the predicate provably warp-uniform: no reconvergence code in the loop below)
             if (!GSX_CELL_REUSE || __any_sync(GSX_FULL, gx != cgx || gy != cgy || gz != cgz)) {
                 cgx = gx, cgy = gy, cgz = gz;
+#endif
                 ps = 0, pc = 0;
                 if (lane < 27) {
                     uint32_t h = probe_hash(gx + pdx, gy + pdy, gz + pdz, n, M, hash_mode);
@@ -896,7 +927,7 @@ static int launch_knn(SorWs& w, int64_t q_begin, int64_t q_end, int K, int hash_
     int64_t grid = (int64_t)sm_count() * (per_sm > 0 ? per_sm : 4);  // persistent: exactly the resident CTAs
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
-    k_sor_knn<NREG, STATS><<<(int)grid, 256, 0, st>>>(w.spos, w.tab_se, w.tab_box, w.caabb, w.saabb, final_means, w.counters,
+    k_sor_knn<NREG, STATS><<<(int)grid, 256, 0, st>>>(w.spos, w.tab_se, w.tab_box, w.cellbits, w.caabb, w.saabb, final_means, w.counters,
                                                       q_begin, q_end, K, hash_mode, bmin[0], bmin[1], bmin[2], cell,
                                                       (uint32_t)w.n, M, stats);
     return GSX_OK;

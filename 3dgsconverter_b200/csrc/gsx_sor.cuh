@@ -15,6 +15,7 @@ struct SorWs {
     int2* tab_se;         // per bucket {start, end} in sorted order; {0,0} = empty (cell_start == -1)
     float4* tab_box;      // per bucket {lo.xyz,-},{hi.xyz,-}: exact box of its points (occupied buckets only)
     uint32_t* startbits;  // one bit per sorted position: starts a bucket
+    uint32_t* cellbits;   // one bit per sorted position: other grid cell than the position before
     float4* caabb;  // 2 float4 per 32-point chunk: {lo.x,lo.y,lo.z,hi.x},{hi.y,hi.z,-,-}
     float4* saabb;  // same per 1024-point super
     float* partial;

@@ -98,7 +98,7 @@ for _name, (_res, _args) in _SIGS.items():
     _fn.argtypes = _args
 
 HASH_MODES = {"i32wrap": 0, "i64": 1}
-KM_ASSIGN = {"auto": 0, "strict": 1, "fma": 2, "tensor": 3, "tensor_tf32": 4}
+KM_ASSIGN = {"auto": 0, "strict": 1, "fma": 2, "tensor": 3, "tensor_bf16": 4}
 
 
 def check(rc: int, what: str = ""):

@@ -212,17 +212,20 @@ int64_t gsx_kmeans_workspace_bytes(int64_t n_total, int32_t nprob, int32_t K, in
  *   STRICT         the contract's distance for every (point, centroid) on the FP32 pipes
  *   FMA_PREFILTER  D >= 9: one fma per (point, centroid, dim) scores every centroid, the strict distance is
  *                  evaluated only for the centroids within a proven rounding-error margin of the best score
- *   TENSOR         the same scheme with the score matrix X.C^T - ||c||^2/2 computed by tcgen05.mma in TMEM: split-bf16
- *                  operands (x = x1 + x2, three kind::f16 MMAs per K step, error 2^-16), accumulator read once with a
- *                  packed-key top-2 epilogue; error if the shape is unsupported (D in {9,24,45}, K <= 256)
- *   TENSOR_TF32    first generation of the tensor-core path (kind::tf32 single product, two-pass epilogue): kept for A/B
+ *   TENSOR         the same scheme with the score matrix X.C^T - ||c||^2/2 computed by tcgen05.mma (kind::tf32, float32
+ *                  accumulators in TMEM, two-pass epilogue: row maximum, candidate mask); error if the shape is
+ *                  unsupported (D in {9,24,45}, K <= 256)
+ *   TENSOR_BF16    variant with split-bf16 operands (x = x1 + x2, three kind::f16 MMAs per K step, score error 2^-16
+ *                  instead of 2^-9, so ~0.2 % instead of ~9 % of the points need a strict evaluation) and a single-pass
+ *                  packed-key top-2 epilogue; measured slower than TENSOR on B200 (the top-2 costs more ALU work than
+ *                  it saves in TMEM reads, profiles/r02_km_tc16_ncu.json) -- kept for A/B
  * tc_stats_dev (may be NULL): 3 uint64 counters accumulated by the TENSOR path {strict distance evaluations,
  * points with more than one candidate, points that needed the full strict scan}. */
 #define GSX_KM_ASSIGN_AUTO 0
 #define GSX_KM_ASSIGN_STRICT 1
 #define GSX_KM_ASSIGN_FMA_PREFILTER 2
 #define GSX_KM_ASSIGN_TENSOR 3
-#define GSX_KM_ASSIGN_TENSOR_TF32 4
+#define GSX_KM_ASSIGN_TENSOR_BF16 4
 int gsx_kmeans_lloyd_device(const float* X_dev, const int64_t* row_off_host, int32_t nprob, int32_t K, int32_t D,
                             int32_t max_iter, float* C_dev, int32_t* labels_dev, int32_t* counts_dev, void* ws,
                             int64_t ws_bytes, int32_t assign_mode, unsigned long long* tc_stats_dev, void* stream);

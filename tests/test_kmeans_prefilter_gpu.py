@@ -6,7 +6,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["fma", "tensor", "tensor_tf32"])
+@pytest.fixture(params=["fma", "tensor", "tensor_bf16"])
 def mode(request, gsx_lib):
     return request.param
 

@@ -44,7 +44,23 @@ def test_tc_full_c3_chunk_matches_oracle(cuda, gsx_lib):
     assert np.array_equal(cnt[0].cpu().numpy(), cnto)
     assert np.allclose(Cc[0].cpu().numpy(), Co, rtol=1e-5, atol=0)
     assert np.array_equal(Cc[0].cpu().numpy().view(np.uint32), Co.view(np.uint32))
-    assert st["full_scans"] == 0 and st["multi_candidate_points"] < 0.02 * 2 * n  # split-bf16 margin: < 2 % ambiguous
+    assert st["full_scans"] == 0 and st["strict_evals"] < 2 * 2 * n  # the margin leaves ~1 candidate per point
+
+
+def test_tc_bf16_variant_margin_is_tight(cuda, gsx_lib):
+    """Split-bf16 scores: the 100x tighter margin leaves < 2 % of the points with more than one candidate."""
+    import torch
+    from gsx import kmeans as gk
+    n, D, K = 400_000, 45, 256
+    g = torch.Generator(device=cuda).manual_seed(9)
+    proto = torch.randn(1024, D, device=cuda, generator=g) * 0.15
+    X = proto[torch.randint(0, 1024, (n,), device=cuda, generator=g)] + 0.03 * torch.randn(n, D, device=cuda, generator=g)
+    init = X[:K].clone().reshape(1, K, D)
+    a = gk.kmeans_lloyd_batched(X, [0, n], K, 2, init, assign="tensor_bf16", want_stats=True)
+    b = gk.kmeans_lloyd_batched(X, [0, n], K, 2, init, assign="tensor", want_stats=True)
+    assert torch.equal(a[1], b[1]) and torch.equal(a[0].view(torch.int32), b[0].view(torch.int32))
+    assert a[3]["full_scans"] == 0 and a[3]["multi_candidate_points"] < 0.02 * 2 * n
+    assert a[3]["multi_candidate_points"] < b[3]["multi_candidate_points"]
 
 
 def test_tc_all_chunks_deterministic_and_equal_to_strict(cuda, gsx_lib):
@@ -58,11 +74,11 @@ def test_tc_all_chunks_deterministic_and_equal_to_strict(cuda, gsx_lib):
         0.03 * torch.randn(nprob * rows, D, device=cuda, generator=g)
     offs = [p * rows for p in range(nprob + 1)]
     init = torch.stack([X[offs[p]:offs[p] + K] for p in range(nprob)])
-    runs = {m: gk.kmeans_lloyd_batched(X, offs, K, 3, init, assign=m) for m in ("tensor", "strict", "fma", "tensor_tf32")}
+    runs = {m: gk.kmeans_lloyd_batched(X, offs, K, 3, init, assign=m) for m in ("tensor", "strict", "fma", "tensor_bf16")}
     again = gk.kmeans_lloyd_batched(X, offs, K, 3, init, assign="tensor")
     for a, b in zip(runs["tensor"], again):
         assert torch.equal(a, b)
-    for m in ("strict", "fma", "tensor_tf32"):
+    for m in ("strict", "fma", "tensor_bf16"):
         assert torch.equal(runs["tensor"][1], runs[m][1])
         assert torch.equal(runs["tensor"][0].view(torch.int32), runs[m][0].view(torch.int32))
         assert torch.equal(runs["tensor"][2], runs[m][2])
