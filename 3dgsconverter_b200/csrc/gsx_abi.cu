@@ -206,7 +206,17 @@ int gsx_sor_mean_dists_range(int64_t n, int64_t q_begin, int64_t q_end, int32_t 
     SorWs w;
     int rc = carve_grid_checked(ws, ws_bytes, n, w);
     if (rc) return rc;
-    return sor_mean_dists(w, q_begin, q_end, k, hash_mode, bmin_host, cell, final_means_dev, stats_dev,
+    return sor_mean_dists(w, q_begin, q_end, 1, 0, k, hash_mode, bmin_host, cell, final_means_dev, stats_dev,
+                          (cudaStream_t)stream);
+}
+
+int gsx_sor_mean_dists_strided(int64_t n, int32_t stride, int32_t phase, int32_t k, int32_t hash_mode,
+                               const float* bmin_host, float cell, void* ws, int64_t ws_bytes, float* final_means_dev,
+                               unsigned long long* stats_dev, void* stream) {
+    SorWs w;
+    int rc = carve_grid_checked(ws, ws_bytes, n, w);
+    if (rc) return rc;
+    return sor_mean_dists(w, 0, n, stride, phase, k, hash_mode, bmin_host, cell, final_means_dev, stats_dev,
                           (cudaStream_t)stream);
 }
 
@@ -257,7 +267,7 @@ int gsx_sor_filter_device(const float* xyz_dev, int64_t n, int32_t k, float thre
     if ((rc = sor_build(xyz_dev, n, mm, cell, w, st))) return rc;
     // the keys buffers are dead after the build: park the means there when the caller wants none
     float* means = means_dev ? means_dev : reinterpret_cast<float*>(w.keys0);
-    if ((rc = sor_mean_dists(w, 0, n, k, hash_mode, mm, cell, means, nullptr, st))) return rc;
+    if ((rc = sor_mean_dists(w, 0, n, 1, 0, k, hash_mode, mm, cell, means, nullptr, st))) return rc;
     if ((rc = mean_std_f32(means, n, w.meanstd, w.ms_ws, w.ms_bytes, st))) return rc;
     return threshold_mask(means, n, w.meanstd, threshold_factor, mask_dev, st);
 }

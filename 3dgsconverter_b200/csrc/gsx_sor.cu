@@ -697,7 +697,8 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
     k_sor_knn(const float4* __restrict__ spos, const int2* __restrict__ tab_se, const float4* __restrict__ tab_box,
               const uint32_t* __restrict__ cellbits, const float4* __restrict__ caabb,
               const float4* __restrict__ saabb, float* __restrict__ final_means, unsigned int* __restrict__ work,
-              int64_t q_begin, int64_t q_end, int K, int hash_mode, float bx, float by, float bz, float cell,
+              int64_t q_begin, int64_t q_end, int q_stride, int q_phase, int K, int hash_mode, float bx, float by,
+              float bz, float cell,
               uint32_t n, uint64_t M, unsigned long long* __restrict__ stats) {
     const int lane = lane_id();
     unsigned long long st_visits = 0, st_scanned = 0, st_boxes = 0, st_queries = 0;
@@ -718,7 +719,9 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
         unsigned int b0 = 0;
         if (lane == 0) b0 = atomicAdd(work, (unsigned)kQueryBatch);
         b0 = __shfl_sync(GSX_FULL, b0, 0);
-        int64_t qb = q_begin + (int64_t)b0;
+        // batch number b0/16 of THIS launch is global batch (b0/16)*q_stride + q_phase: with q_stride = number of ranks the
+        // batches are dealt round-robin, so every rank samples the whole hash range (cost-balanced, see dist.py)
+        int64_t qb = q_begin + ((int64_t)(b0 / kQueryBatch) * q_stride + q_phase) * kQueryBatch;
         if (qb >= q_end) break;
         int64_t qe = qb + kQueryBatch < q_end ? qb + kQueryBatch : q_end;
         // the 27 probes of a query depend only on its cell: consecutive hash-sorted queries mostly share
@@ -920,7 +923,8 @@ __global__ void k_fill_f32(float* p, int64_t n, float v) {
 }
 
 template <int NREG, bool STATS>
-static int launch_knn(SorWs& w, int64_t q_begin, int64_t q_end, int K, int hash_mode, const float* bmin, float cell,
+static int launch_knn(SorWs& w, int64_t q_begin, int64_t q_end, int q_stride, int q_phase, int K, int hash_mode,
+                      const float* bmin, float cell,
                       float* final_means, unsigned long long* stats, uint64_t M, int64_t want, cudaStream_t st) {
     int per_sm = 0;
     GSX_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sor_knn<NREG, STATS>, 256, 0));
@@ -928,18 +932,21 @@ static int launch_knn(SorWs& w, int64_t q_begin, int64_t q_end, int K, int hash_
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
     k_sor_knn<NREG, STATS><<<(int)grid, 256, 0, st>>>(w.spos, w.tab_se, w.tab_box, w.cellbits, w.caabb, w.saabb, final_means, w.counters,
-                                                      q_begin, q_end, K, hash_mode, bmin[0], bmin[1], bmin[2], cell,
+                                                      q_begin, q_end, q_stride, q_phase, K, hash_mode, bmin[0], bmin[1],
+                                                      bmin[2], cell,
                                                       (uint32_t)w.n, M, stats);
     return GSX_OK;
 }
 
-int sor_mean_dists(SorWs& w, int64_t q_begin, int64_t q_end, int k, int hash_mode, const float* bmin, float cell,
+int sor_mean_dists(SorWs& w, int64_t q_begin, int64_t q_end, int q_stride, int q_phase, int k, int hash_mode,
+                   const float* bmin, float cell,
                    float* final_means, unsigned long long* stats, cudaStream_t st) {
     GSX_NVTX("gsx::sor_mean_dists(k_sor_knn)");
     int64_t n = w.n;
     GSX_REQUIRE(k >= 1, GSX_ERR_ARG, "sor: k must be >= 1 (got %d)", k);
     GSX_REQUIRE(hash_mode == 0 || hash_mode == 1, GSX_ERR_ARG, "sor: bad hash_mode %d", hash_mode);
     GSX_REQUIRE(q_begin >= 0 && q_end <= n && q_begin <= q_end, GSX_ERR_ARG, "sor: bad query range");
+    GSX_REQUIRE(q_stride >= 1 && q_phase >= 0 && q_phase < q_stride, GSX_ERR_ARG, "sor: bad query stride/phase");
     int K = k < 50 ? k : 50;  // gpu_ops.py:244
     if (q_end == q_begin) return GSX_OK;
     if (!(cell > 1e-8f)) {  // gpu_ops.py:175-176 (unreachable through the driver: cell >= 1e-4)
@@ -950,13 +957,13 @@ int sor_mean_dists(SorWs& w, int64_t q_begin, int64_t q_end, int k, int hash_mod
     }
     GSX_CUDA_CHECK(cudaMemsetAsync(w.counters, 0, sizeof(unsigned int), st));
     uint64_t M = 0xFFFFFFFFFFFFFFFFull / (uint64_t)n + 1ull;
-    int64_t nq = q_end - q_begin;
+    int64_t nq = (q_end - q_begin + q_stride - 1) / q_stride + kQueryBatch;   // this launch's share (upper bound)
     int64_t want = (nq + (int64_t)kQueryBatch * 8 - 1) / ((int64_t)kQueryBatch * 8);
     int rc;
-    if (stats) rc = K <= 32 ? launch_knn<1, true>(w, q_begin, q_end, K, hash_mode, bmin, cell, final_means, stats, M, want, st)
-                            : launch_knn<2, true>(w, q_begin, q_end, K, hash_mode, bmin, cell, final_means, stats, M, want, st);
-    else rc = K <= 32 ? launch_knn<1, false>(w, q_begin, q_end, K, hash_mode, bmin, cell, final_means, stats, M, want, st)
-                      : launch_knn<2, false>(w, q_begin, q_end, K, hash_mode, bmin, cell, final_means, stats, M, want, st);
+    if (stats) rc = K <= 32 ? launch_knn<1, true>(w, q_begin, q_end, q_stride, q_phase, K, hash_mode, bmin, cell, final_means, stats, M, want, st)
+                            : launch_knn<2, true>(w, q_begin, q_end, q_stride, q_phase, K, hash_mode, bmin, cell, final_means, stats, M, want, st);
+    else rc = K <= 32 ? launch_knn<1, false>(w, q_begin, q_end, q_stride, q_phase, K, hash_mode, bmin, cell, final_means, stats, M, want, st)
+                      : launch_knn<2, false>(w, q_begin, q_end, q_stride, q_phase, K, hash_mode, bmin, cell, final_means, stats, M, want, st);
     if (rc) return rc;
     GSX_KERNEL_CHECK();
     return GSX_OK;

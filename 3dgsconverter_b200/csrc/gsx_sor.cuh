@@ -37,7 +37,8 @@ int64_t sor_grid_workspace_bytes(int64_t n);
 size_t sor_sort_ws_bytes(int64_t n);
 int sor_minmax(const float* xyz, int64_t n, float* minmax_dev, float* partial, cudaStream_t st);
 int sor_build(const float* xyz, int64_t n, const float* bmin, float cell, SorWs& w, cudaStream_t st);
-int sor_mean_dists(SorWs& w, int64_t q_begin, int64_t q_end, int k, int hash_mode, const float* bmin, float cell,
+int sor_mean_dists(SorWs& w, int64_t q_begin, int64_t q_end, int q_stride, int q_phase, int k, int hash_mode,
+                   const float* bmin, float cell,
                    float* final_means, unsigned long long* stats, cudaStream_t st);
 
 int sor_dist_local_run(const float* xyz, int64_t n_local, int64_t idx_base, int64_t n_global, int world,

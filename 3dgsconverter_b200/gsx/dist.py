@@ -13,8 +13,9 @@ cells hash to arbitrary buckets, so a halo exchange cannot reproduce it (SURVEY 
      global hash-sorted array; the slots are exchanged with one grouped batch of point-to-point sends
      (an all-gather with ragged segment sizes and no staging copy);
   5. C: bucket table, bucket boxes and chunk/super boxes from the sorted array (two streaming passes, replicated);
-  6. rank r queries exactly ITS OWN segment of the sorted order (neighbouring queries share buckets) and writes
-     the mean distances at the global original indices of a zero-filled vector;
+  6. the sorted order is cut into batches of 16 queries dealt round-robin over the ranks (cost-balanced: every rank
+     samples the whole hash range); each rank writes its mean distances at the global original indices of a
+     zero-filled vector;
   7. reduce-scatter(sum) of that vector to the slab owners -- every entry has exactly one writer, so x+0 is exact
      (half the traffic of the all-reduce of round 1); ragged slabs fall back to all-reduce + slice;
   8. NumPy-order mean/std of the GLOBAL vector without gathering it: every rank sums the pairwise-tree leaves that
@@ -178,6 +179,10 @@ class _GsxSorOps:
         from . import sor
         sor.mean_dists(grid, k, hash_mode, out=out, q_range=(qb, qe))
 
+    def mean_dists_strided(self, grid, k, hash_mode, out, stride, phase):
+        from . import sor
+        sor.mean_dists_strided(grid, k, hash_mode, out, stride, phase)
+
     def mask_from_means(self, means, threshold_factor):
         from . import sor
         return sor.threshold_mask(means, sor.mean_std(means), threshold_factor)
@@ -324,11 +329,11 @@ def sor_filter_distributed(xyz_local: torch.Tensor, k: int = 25, threshold_facto
     st = _Stamps(timings is not None, dev)
     grid, sizes, seg_sizes = build_grid_distributed(xyz_local, group, ops=build_ops or ops, stamps=st)
     n = int(sum(sizes))
-    qb = int(sum(seg_sizes[:rank]))
-    qe = qb + seg_sizes[rank]
     means_full = torch.zeros(n, dtype=torch.float32, device=dev)
-    if qe > qb:
-        ops.mean_dists_range(grid, k, hash_mode, means_full, qb, qe)
+    # batches of 16 consecutive sorted positions dealt round-robin over the ranks: every rank samples the whole hash
+    # range, so the expensive clustered buckets do not all land on the owner of their hash range (measured at N=4:
+    # slowest rank 8.7 ms vs 6.6 ms mean with contiguous segments)
+    ops.mean_dists_strided(grid, k, hash_mode, means_full, dist.get_world_size(group), rank)
     st.mark("knn")
     means_local = route_to_slabs(means_full, sizes, rank, group)
     st.mark("nccl_route_means")

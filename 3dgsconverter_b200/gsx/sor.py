@@ -87,6 +87,20 @@ def mean_dists(grid: SorGrid, k: int, hash_mode: str | None = None, out: torch.T
     return out
 
 
+def mean_dists_strided(grid: SorGrid, k: int, hash_mode: str | None, out: torch.Tensor, stride: int, phase: int,
+                       want_stats: bool = False):
+    """Queries the 16-position batches b with b % stride == phase (cost-balanced multi-GPU sharding)."""
+    mode = HASH_MODES[hash_mode or default_hash_mode()]
+    stats = torch.zeros(4, dtype=torch.int64, device=out.device) if want_stats else None
+    check(lib.gsx_sor_mean_dists_strided(grid.n, int(stride), int(phase), int(k), mode,
+                                         grid.bmin.ctypes.data_as(C.POINTER(C.c_float)), grid.cell, _ptr(grid.ws),
+                                         grid.ws.numel(), _ptr(out), _ptr(stats), _stream()), "gsx_sor_mean_dists_strided")
+    if want_stats:
+        v = stats.cpu().numpy()
+        return out, dict(visits=int(v[0]), scanned=int(v[1]), box_tests=int(v[2]), queries=int(v[3]))
+    return out
+
+
 def mean_std(a: torch.Tensor) -> torch.Tensor:
     """np.mean / np.std (float32 pairwise) of a float32 CUDA vector -> tensor [mean, std] on device."""
     n = a.numel()

@@ -408,9 +408,8 @@ def run_c2(args):
         _, st = sor.mean_dists(grid, K_SOR, args.hash, out=means, want_stats=True)
     else:
         grid, sizes, seg = gd.build_grid_distributed(xyz)
-        qb = int(sum(seg[:rank]))
         tmp = torch.zeros(n_total, dtype=torch.float32, device=dev)
-        _, st = sor.mean_dists(grid, K_SOR, args.hash, out=tmp, want_stats=True, q_range=(qb, qb + seg[rank]))
+        _, st = sor.mean_dists_strided(grid, K_SOR, args.hash, tmp, world, rank, want_stats=True)
         del tmp, grid
     pk = peaks()
     hbm = float(pk.get("hbm_gbs", 6650.0))

@@ -97,6 +97,14 @@ int gsx_sor_mean_dists_range(int64_t n, int64_t q_begin, int64_t q_end, int32_t 
                              const float* bmin_host, float cell, void* ws, int64_t ws_bytes, float* final_means_dev,
                              unsigned long long* stats_dev, void* stream);
 
+/* Multi-GPU variant with COST-balanced sharding: the hash-sorted positions are cut into batches of 16; this call
+ * queries the batches b with b % stride == phase (stride = number of ranks, phase = rank), so every rank samples the
+ * whole hash range -- the expensive (clustered) buckets are spread over all ranks instead of falling to the owner of
+ * their hash range.  Rows of final_means_dev belonging to other batches are left untouched. */
+int gsx_sor_mean_dists_strided(int64_t n, int32_t stride, int32_t phase, int32_t k, int32_t hash_mode,
+                               const float* bmin_host, float cell, void* ws, int64_t ws_bytes, float* final_means_dev,
+                               unsigned long long* stats_dev, void* stream);
+
 /* gpu_ops.py:227 (np.argsort of the bucket hashes): stable LSD radix sort, in place, of (uint64 key, int32
  * value) pairs on the key bits [begin_bit, end_bit).  The hash-grid build uses it with key =
  * hash << 15 | Morton code and value = original index. */

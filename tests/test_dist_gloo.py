@@ -307,6 +307,15 @@ class OracleQueryOps(OracleOps):
                                         {"i32wrap": 0, "i64": 1}[hash_mode or "i32wrap"], None)
         out.numpy()[orig[qb:qe]] = md[qb:qe]
 
+    def mean_dists_strided(self, grid, k, hash_mode, out, stride, phase):
+        n = grid["n"]
+        full = torch.zeros(n, dtype=torch.float32)
+        self.mean_dists_range(grid, k, hash_mode, full, 0, n)           # all queries, then keep this rank's batches
+        orig = grid["spos"][:, 3].copy().view(np.int32)
+        pos = np.arange(n)
+        mine = ((pos // 16) % stride) == phase
+        out.numpy()[orig[mine]] = full.numpy()[orig[mine]]
+
 
 class OracleDistOps(OracleQueryOps, OracleBuildOps):
     pass

@@ -73,14 +73,29 @@ def test_owner_partition_formula(gsx_lib):
 def test_bench_reference_arm_line():
     """`bench.py --impl reference` prints one JSON line with the contract's keys (tiny sample, CPU only)."""
     out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--cpu-sample", "20000", "--n", "20000"], capture_output=True, text=True, timeout=300)
+                          "--splats-per-gpu", "20000"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "Msplats/s" and line["value"] > 0
+    # same `config` object as the gsx arm prints for this workload (the driver compares them)
+    assert line["config"] == {"workload": "0M-splat mixed cloud per GPU (SURVEY 8d generator), SOR k=16 sigma=2.0; global "
+                                          "filter over the union cloud of 20000 splats", "splats_per_gpu": 20000, "k": 16,
+                              "sigma": 2.0, "cloud": "mixed"}
+    assert line["cpu_baseline"]["sample_points"] == 20000
     for key in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "config", "e2e",
                 "cpu_baseline"):
         assert key in line
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_bench_reference_arm_does_not_load_libgsx():
+    """the reference arm's process must not map libgsx.so (the generator is loaded as a file)."""
+    code = ("import sys, runpy; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0', "
+            "'--splats-per-gpu', '5000']; runpy.run_path(r'%s', run_name='__main__'); "
+            "maps = open('/proc/self/maps').read(); assert 'libgsx' not in maps, 'libgsx.so mapped'; "
+            "assert 'gsx' not in sys.modules and 'torch' not in sys.modules") % str(ROOT / "bench.py")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
 
 
 def test_dropin_mirror_has_reference_surface():
