@@ -180,7 +180,7 @@ def kmeans(data: np.ndarray, k: int, max_iter=10, tolerance=1e-4, use_gpu=True, 
         if r is not None:
             return r
     batch_stats["single_calls"] += 1
-    x = data.astype(np.float32)
+    x = data.astype(np.float32, copy=False)   # (the reference copies, gpu_ops.py:181; same values, 140 MB less traffic)
     # exactly the reference's draw from the global NumPy RNG (gpu_ops.py:182) so np.random.seed reproduces
     init = x[np.random.choice(n, k, replace=False)].astype(np.float32)
     centroids, labels = _km.kmeans_host(x, int(k), int(max_iter), init)
