@@ -176,13 +176,13 @@ int gsx_sor_dist_local_run(const float* xyz_local_dev, int64_t n_local, int64_t 
 }
 
 int gsx_sor_dist_merge(const float* pos4_dev, int64_t m, int64_t n_global, const float* bmin_host, float cell,
-                       float* pos4_sorted_dev, void* ws, int64_t ws_bytes, void* stream) {
+                       float* pos4_sorted_dev, uint8_t* flags_sorted_dev, void* ws, int64_t ws_bytes, void* stream) {
     if (m == 0) return GSX_OK;
     SorWs w;
     int rc = carve_checked(ws, ws_bytes, m, w);
     if (rc) return rc;
-    return sor_dist_merge((const float4*)pos4_dev, m, n_global, bmin_host, cell, (float4*)pos4_sorted_dev, w,
-                          (cudaStream_t)stream);
+    return sor_dist_merge((const float4*)pos4_dev, m, n_global, bmin_host, cell, (float4*)pos4_sorted_dev,
+                          flags_sorted_dev, w, (cudaStream_t)stream);
 }
 
 int64_t gsx_sor_spos_offset(int64_t n) {
@@ -191,13 +191,13 @@ int64_t gsx_sor_spos_offset(int64_t n) {
     return (int64_t)((char*)w.spos - (char*)nullptr);
 }
 
-int gsx_sor_build_from_sorted(const float* spos4_dev, int64_t n, const float* bmin_host, float cell, void* ws,
-                              int64_t ws_bytes, void* stream) {
+int gsx_sor_build_from_sorted(const float* spos4_dev, const uint8_t* flags_dev, int64_t n, const float* bmin_host,
+                              float cell, void* ws, int64_t ws_bytes, void* stream) {
     SorWs w;
     int rc = carve_grid_checked(ws, ws_bytes, n, w);
     if (rc) return rc;
     GSX_REQUIRE(cell > 0.f, GSX_ERR_ARG, "sor: cell size must be > 0");
-    return sor_build_from_sorted((const float4*)spos4_dev, n, bmin_host, cell, w, (cudaStream_t)stream);
+    return sor_build_from_sorted((const float4*)spos4_dev, flags_dev, n, bmin_host, cell, w, (cudaStream_t)stream);
 }
 
 int gsx_sor_mean_dists_range(int64_t n, int64_t q_begin, int64_t q_end, int32_t k, int32_t hash_mode,

@@ -407,6 +407,83 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// Stage C when the owners shipped per-point flags (bit 0 bucket start, bit 1 cell change): a pure streaming pass --
+// chunk / super boxes, the two bit masks, and the {start,end} table entries.  Only bucket boundaries need the hash;
+// they are ~1 in 32 positions, so they are compacted through shared memory and hashed by as few warps as possible
+// instead of every warp issuing the hash for one or two active lanes.
+__global__ void __launch_bounds__(1024)
+    k_sor_finish_flags(const float4* __restrict__ spos, const uint8_t* __restrict__ flags, int64_t n, float bx, float by,
+                       float bz, float cell, uint64_t M64, int2* __restrict__ tab_se, uint32_t* __restrict__ startbits,
+                       uint32_t* __restrict__ cellbits, float4* __restrict__ caabb, float4* __restrict__ saabb) {
+    const int64_t j = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    const int lane = lane_id();
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    bool start = false, end = false, newcell = false;
+    if (j < n) {
+        const float4 p = spos[j];
+        lo[0] = hi[0] = p.x;
+        lo[1] = hi[1] = p.y;
+        lo[2] = hi[2] = p.z;
+        const uint8_t f = flags[j];
+        start = (f & 1) != 0;
+        newcell = (f & 2) != 0;
+        end = j == n - 1 || (flags[j + 1] & 1) != 0;
+    }
+    const unsigned sb = __ballot_sync(GSX_FULL, start), cb = __ballot_sync(GSX_FULL, newcell);
+    // boundary list of this block: entries = position << 1 | is_end
+    __shared__ unsigned s_cnt;
+    __shared__ unsigned s_list[2048];
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    if (start) s_list[atomicAdd(&s_cnt, 1u)] = (unsigned)threadIdx.x << 1;
+    if (end) s_list[atomicAdd(&s_cnt, 1u)] = ((unsigned)threadIdx.x << 1) | 1u;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        lo[a] = ord_to_float(__reduce_min_sync(GSX_FULL, float_to_ord(lo[a])));
+        hi[a] = ord_to_float(__reduce_max_sync(GSX_FULL, float_to_ord(hi[a])));
+    }
+    __shared__ float sm[6][32];
+    const int w = threadIdx.x >> 5;
+    const int64_t chunk = (int64_t)blockIdx.x * 32 + w;
+    if (lane == 0) {
+        if (chunk * 32 < n) {
+            startbits[chunk] = sb;
+            cellbits[chunk] = cb;
+            caabb[2 * chunk] = make_float4(lo[0], lo[1], lo[2], hi[0]);
+            caabb[2 * chunk + 1] = make_float4(hi[1], hi[2], 0.f, 0.f);
+        }
+        for (int a = 0; a < 3; ++a) {
+            sm[a][w] = lo[a];
+            sm[3 + a][w] = hi[a];
+        }
+    }
+    __syncthreads();
+    // hash only the boundary positions (compacted: ~64 per block)
+    for (unsigned t = threadIdx.x; t < s_cnt; t += 1024) {
+        const unsigned e = s_list[t];
+        const int64_t pj = (int64_t)blockIdx.x * 1024 + (e >> 1);
+        const float4 p = spos[pj];
+        const uint32_t h = bucket_of(p.x, p.y, p.z, bx, by, bz, cell, n, M64);
+        if (e & 1u) tab_se[h].y = (int)(pj + 1); else tab_se[h].x = (int)pj;
+    }
+    if (w == 0) {
+        float v[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            v[a] = sm[a][lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                float t = __shfl_xor_sync(GSX_FULL, v[a], o);
+                v[a] = a < 3 ? fminf(v[a], t) : fmaxf(v[a], t);
+            }
+        }
+        if (lane == 0) {
+            saabb[2 * (int64_t)blockIdx.x] = make_float4(v[0], v[1], v[2], v[3]);
+            saabb[2 * (int64_t)blockIdx.x + 1] = make_float4(v[4], v[5], 0.f, 0.f);
+        }
+    }
+}
+
 // table, boxes and bucket boxes from the sorted order (shared tail of the single-GPU and the distributed build)
 template <bool GATHER>
 static int sor_finish(const float* xyz, int64_t n, const float* bmin, float cell, SorWs& w, cudaStream_t st) {
@@ -529,8 +606,35 @@ __global__ void __launch_bounds__(256) k_sor_keys_pos4(const float4* __restrict_
     vals[i] = (int32_t)i;
 }
 
+// stage B output with per-point flags for stage C: bit 0 = this sorted point starts a bucket, bit 1 = its grid cell
+// differs from the previous sorted point's (first point of a segment: both).  The owner knows the sorted keys, so
+// the ranks that receive the segment do not have to re-hash every point (their stage C is replicated work).
+__global__ void __launch_bounds__(256)
+    k_owner_gather_flags(const float4* __restrict__ in, const int32_t* __restrict__ order,
+                         const uint64_t* __restrict__ keys_sorted, int64_t m, float bx, float by, float bz, float cell,
+                         float4* __restrict__ out, uint8_t* __restrict__ flags) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ int sh_c[3][256];
+    int gx = 0x7fffffff, gy = 0, gz = 0;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < m) {
+        p = in[order[j]];
+        out[j] = p;
+        gx = (int)floorf(__fdiv_rn(__fsub_rn(p.x, bx), cell));
+        gy = (int)floorf(__fdiv_rn(__fsub_rn(p.y, by), cell));
+        gz = (int)floorf(__fdiv_rn(__fsub_rn(p.z, bz), cell));
+    }
+    sh_c[0][threadIdx.x] = gx, sh_c[1][threadIdx.x] = gy, sh_c[2][threadIdx.x] = gz;
+    __syncthreads();
+    if (j >= m) return;
+    const bool start = j == 0 || (keys_sorted[j] >> kMortonBits) != (keys_sorted[j - 1] >> kMortonBits);
+    bool newcell = threadIdx.x == 0 || sh_c[0][threadIdx.x - 1] != gx || sh_c[1][threadIdx.x - 1] != gy ||
+                   sh_c[2][threadIdx.x - 1] != gz;   // block edges: conservatively "new"
+    flags[j] = (uint8_t)((start ? 1 : 0) | ((newcell || start) ? 2 : 0));
+}
+
 int sor_dist_merge(const float4* pos4_in, int64_t m, int64_t n_global, const float* bmin, float cell, float4* pos4_out,
-                   SorWs& w, cudaStream_t st) {
+                   uint8_t* flags_out, SorWs& w, cudaStream_t st) {
     GSX_NVTX("gsx::sor_dist_merge");
     if (m == 0) return GSX_OK;
     int blocks = (int)((m + 255) / 256);
@@ -542,19 +646,33 @@ int sor_dist_merge(const float4* pos4_in, int64_t m, int64_t n_global, const flo
     int rc = radix_sort_pairs(w.keys0, w.keys1, w.vals0, w.vals1, m, 0, kMortonBits + hash_bits_of(n_global), w.sort_ws,
                               w.sort_ws_bytes, &ks, &order, st);
     if (rc) return rc;
-    k_gather4<<<blocks, 256, 0, st>>>(pos4_in, order, m, pos4_out);
+    if (flags_out)
+        k_owner_gather_flags<<<blocks, 256, 0, st>>>(pos4_in, order, ks, m, bmin[0], bmin[1], bmin[2], cell, pos4_out,
+                                                     flags_out);
+    else
+        k_gather4<<<blocks, 256, 0, st>>>(pos4_in, order, m, pos4_out);
     GSX_KERNEL_CHECK();
     return GSX_OK;
 }
 
 // stage C: everything gsx_sor_build produces, from an already hash-sorted float4 array
-int sor_build_from_sorted(const float4* spos_in, int64_t n, const float* bmin, float cell, SorWs& w, cudaStream_t st) {
+int sor_build_from_sorted(const float4* spos_in, const uint8_t* flags, int64_t n, const float* bmin, float cell, SorWs& w,
+                          cudaStream_t st) {
     GSX_NVTX("gsx::sor_build_from_sorted");
     if (spos_in != w.spos)
         GSX_CUDA_CHECK(cudaMemcpyAsync(w.spos, spos_in, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, st));
     w.keys_sorted = nullptr;
     w.order = nullptr;
-    return sor_finish<false>(nullptr, n, bmin, cell, w, st);
+    if (!flags) return sor_finish<false>(nullptr, n, bmin, cell, w, st);
+    const uint64_t M64 = 0xFFFFFFFFFFFFFFFFull / (uint64_t)n;
+    GSX_CUDA_CHECK(cudaMemsetAsync(w.tab_se, 0, (size_t)n * sizeof(int2), st));
+    k_sor_finish_flags<<<(int)((n + 1023) / 1024), 1024, 0, st>>>(w.spos, flags, n, bmin[0], bmin[1], bmin[2], cell, M64,
+                                                                  w.tab_se, w.startbits, w.cellbits, w.caabb, w.saabb);
+    GSX_KERNEL_CHECK();
+    k_sor_bucket_boxes<<<(int)((n + 255) / 256), 256, 0, st>>>(w.startbits, w.spos, w.caabb, w.tab_se, n, bmin[0],
+                                                               bmin[1], bmin[2], cell, M64, w.tab_box);
+    GSX_KERNEL_CHECK();
+    return GSX_OK;
 }
 
 // ------------------------------------------------------------------ query kernel

@@ -45,8 +45,9 @@ int sor_dist_local_run(const float* xyz, int64_t n_local, int64_t idx_base, int6
                        const float* bmin, float cell, float4* pos4_out, long long* cuts_dev, SorWs& w,
                        cudaStream_t st);
 int sor_dist_merge(const float4* pos4_in, int64_t m, int64_t n_global, const float* bmin, float cell, float4* pos4_out,
-                   SorWs& w, cudaStream_t st);
-int sor_build_from_sorted(const float4* spos_in, int64_t n, const float* bmin, float cell, SorWs& w, cudaStream_t st);
+                   uint8_t* flags_out, SorWs& w, cudaStream_t st);
+int sor_build_from_sorted(const float4* spos_in, const uint8_t* flags, int64_t n, const float* bmin, float cell, SorWs& w,
+                          cudaStream_t st);
 
 size_t mean_std_ws_bytes(int64_t n);
 int mean_std_f32(const float* a, int64_t n, float* out_dev, void* ws, size_t ws_bytes, cudaStream_t st);

@@ -69,21 +69,24 @@ def _global_rank(group, r):
     return dist.get_global_rank(group, r) if group is not None else r
 
 
-def exchange_segments(buf: torch.Tensor, seg_sizes, rank: int, group=None):
-    """All-gather with ragged segment sizes, in place: `buf` [sum(seg_sizes), C] already holds this rank's segment at
-    its offset; one grouped batch of point-to-point operations sends it to every peer and receives the peers'
-    segments straight into their slots (NCCL runs the batch as one group = an all-to-all pattern over NVSwitch)."""
+def exchange_segments(bufs, seg_sizes, rank: int, group=None):
+    """All-gather with ragged segment sizes, in place: every `buf` [sum(seg_sizes), ...] of `bufs` (one tensor or a
+    list with the same row partition) already holds this rank's segment at its offset; ONE grouped batch of
+    point-to-point operations sends the segments to every peer and receives the peers' segments straight into their
+    slots (NCCL runs the batch as one group = an all-to-all pattern over NVSwitch)."""
+    if isinstance(bufs, torch.Tensor):
+        bufs = [bufs]
     world = len(seg_sizes)
     bases = np.concatenate([[0], np.cumsum(seg_sizes)]).astype(np.int64)
-    mine = buf[bases[rank]: bases[rank + 1]]
     ops = []
     for step in range(1, world):
         dst = (rank + step) % world
         src = (rank - step) % world
-        if seg_sizes[rank] > 0:
-            ops.append(dist.P2POp(dist.isend, mine, _global_rank(group, dst), group))
-        if seg_sizes[src] > 0:
-            ops.append(dist.P2POp(dist.irecv, buf[bases[src]: bases[src + 1]], _global_rank(group, src), group))
+        for buf in bufs:
+            if seg_sizes[rank] > 0:
+                ops.append(dist.P2POp(dist.isend, buf[bases[rank]: bases[rank + 1]], _global_rank(group, dst), group))
+            if seg_sizes[src] > 0:
+                ops.append(dist.P2POp(dist.irecv, buf[bases[src]: bases[src + 1]], _global_rank(group, src), group))
     if ops:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
@@ -140,8 +143,9 @@ class _GsxSorOps:
                                          _ptr(ws_l), ws_l.numel(), _stream()), "gsx_sor_dist_local_run")
         return pos4, cuts
 
-    def merge_into(self, pos4_r, n_global, bmin, cell, out):
-        """B: sort the received points of this rank's bucket range by (bucket, in-cell Morton) into `out`."""
+    def merge_into(self, pos4_r, n_global, bmin, cell, out, flags_out=None):
+        """B: sort the received points of this rank's bucket range by (bucket, in-cell Morton) into `out`; with
+        `flags_out` (uint8 per point) also the bucket-start / cell-change flags stage C consumes."""
         import ctypes as C
         from . import sor
         from ._abi import lib, check
@@ -151,7 +155,8 @@ class _GsxSorOps:
             return
         ws_m = sor.workspace(m, pos4_r.device)
         check(lib.gsx_sor_dist_merge(_ptr(pos4_r), m, n_global, bmin.ctypes.data_as(C.POINTER(C.c_float)), cell,
-                                     _ptr(out), _ptr(ws_m), ws_m.numel(), _stream()), "gsx_sor_dist_merge")
+                                     _ptr(out), _ptr(flags_out), _ptr(ws_m), ws_m.numel(), _stream()),
+              "gsx_sor_dist_merge")
 
     def new_grid_storage(self, n_global, dev):
         """Workspace of the final grid and a [n_global,4] view of its sorted-position array (exchange target)."""
@@ -160,14 +165,15 @@ class _GsxSorOps:
         off = lib.gsx_sor_spos_offset(n_global)
         return ws, ws[off: off + n_global * 16].view(torch.float32).view(n_global, 4)
 
-    def finish(self, ws, spos_full, n_global, bmin, cell):
-        """C: table, boxes and bucket boxes from the globally sorted array."""
+    def finish(self, ws, spos_full, n_global, bmin, cell, flags_full=None):
+        """C: table, boxes and bucket boxes from the globally sorted array (and the owners' flags, if exchanged)."""
         import ctypes as C
         from . import sor
         from ._abi import lib, check
         from .sor import _ptr, _stream
-        check(lib.gsx_sor_build_from_sorted(_ptr(spos_full), n_global, bmin.ctypes.data_as(C.POINTER(C.c_float)), cell,
-                                            _ptr(ws), ws.numel(), _stream()), "gsx_sor_build_from_sorted")
+        check(lib.gsx_sor_build_from_sorted(_ptr(spos_full), _ptr(flags_full), n_global,
+                                            bmin.ctypes.data_as(C.POINTER(C.c_float)), cell, _ptr(ws), ws.numel(),
+                                            _stream()), "gsx_sor_build_from_sorted")
         return sor.SorGrid(n_global, ws, bmin, cell)
 
     # replicated-build path
@@ -309,12 +315,13 @@ def build_grid_distributed(xyz_local: torch.Tensor, group=None, ops=None, stamps
     st.mark("nccl_all_to_all")
     # 4. B: owner sort straight into the slot, then the ragged all-gather of the slots
     ws, spos_full = ops.new_grid_storage(n_global, dev)
-    ops.merge_into(pos4_r, n_global, bmin, cell, spos_full[seg_base: seg_base + m])
+    flags_full = torch.empty(n_global, dtype=torch.uint8, device=dev)   # bit 0 bucket start, bit 1 cell change
+    ops.merge_into(pos4_r, n_global, bmin, cell, spos_full[seg_base: seg_base + m], flags_full[seg_base: seg_base + m])
     st.mark("build_B_owner_sort")
-    exchange_segments(spos_full, seg_sizes, rank, group)
+    exchange_segments([spos_full, flags_full], seg_sizes, rank, group)
     st.mark("nccl_segments")
-    # 5. C: table, boxes, bucket boxes -- replicated, two streaming passes over n_global
-    grid = ops.finish(ws, spos_full, n_global, bmin, cell)
+    # 5. C: table, boxes, bucket boxes -- replicated, two streaming passes over n_global (no re-hash: owners' flags)
+    grid = ops.finish(ws, spos_full, n_global, bmin, cell, flags_full)
     st.mark("build_C_table_boxes")
     return grid, sizes, seg_sizes
 

@@ -69,7 +69,10 @@ int gsx_sor_build(const float* xyz_dev, int64_t n, const float* bmin_host, float
  *     {x,y,z, bits(idx_base + local index)} grouped by owner and cuts_dev[G+1] = first position of every owner
  *     -> the caller exchanges the groups (all-to-all).
  *  B. merge:      sorts the m received points of this rank's bucket range by (bucket, in-cell Morton)
- *     -> the caller all-gathers the segments in owner order = the globally hash-sorted array.
+ *     -> the caller all-gathers the segments in owner order = the globally hash-sorted array.  With flags_sorted_dev
+ *     the owner also emits one byte per sorted point (bit 0: starts a bucket, bit 1: other grid cell than the point
+ *     before) -- exchanged along with the segment (1 B/pt next to 16 B/pt), it spares every receiving rank the
+ *     re-hash of every point in its replicated stage C.
  *  C. build_from_sorted: bucket table ({start,end} per bucket, 8 B, the only part that is pre-zeroed), bucket boxes
  *     and chunk/super boxes from that array in one fused pass + one pass over the bucket starts (what
  *     gsx_sor_build leaves in the workspace), after which gsx_sor_mean_dists[_range] can run.  If spos4_dev already points at
@@ -79,10 +82,11 @@ int gsx_sor_dist_local_run(const float* xyz_local_dev, int64_t n_local, int64_t 
                            int32_t world, const float* bmin_host, float cell, float* pos4_out_dev,
                            int64_t* cuts_dev, void* ws, int64_t ws_bytes, void* stream);
 int gsx_sor_dist_merge(const float* pos4_dev, int64_t m, int64_t n_global, const float* bmin_host, float cell,
-                       float* pos4_sorted_dev, void* ws, int64_t ws_bytes, void* stream);
+                       float* pos4_sorted_dev, uint8_t* flags_sorted_dev /* uint8[m] or NULL */, void* ws,
+                       int64_t ws_bytes, void* stream);
 int64_t gsx_sor_spos_offset(int64_t n);
-int gsx_sor_build_from_sorted(const float* spos4_dev, int64_t n, const float* bmin_host, float cell, void* ws,
-                              int64_t ws_bytes, void* stream);
+int gsx_sor_build_from_sorted(const float* spos4_dev, const uint8_t* flags_dev /* uint8[n] or NULL */, int64_t n,
+                              const float* bmin_host, float cell, void* ws, int64_t ws_bytes, void* stream);
 
 /* gpu_ops.py:98-176 + :255-256: K = min(k,50) nearest candidates over the 27 probed buckets, mean of
  * their distances, written in the caller's point order (the "unsort" is fused).  Must follow

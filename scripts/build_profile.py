@@ -27,7 +27,7 @@ sp2.copy_(spos)
 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
 for it in range(3):
     ev[0].record()
-    check(lib.gsx_sor_build_from_sorted(_ptr(sp2), n, grid.bmin.ctypes.data_as(C.POINTER(C.c_float)), grid.cell, _ptr(gws),
+    check(lib.gsx_sor_build_from_sorted(_ptr(sp2), None, n, grid.bmin.ctypes.data_as(C.POINTER(C.c_float)), grid.cell, _ptr(gws),
                                         gws.numel(), _stream()))
     ev[1].record()
     torch.cuda.synchronize()

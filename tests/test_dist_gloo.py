@@ -271,18 +271,29 @@ class OracleBuildOps:
         cuts = np.searchsorted(owner[order], np.arange(world + 1))
         return torch.from_numpy(pos4), torch.from_numpy(cuts.astype(np.int64))
 
-    def merge_into(self, pos4_r, n_global, bmin, cell, out):
+    def merge_into(self, pos4_r, n_global, bmin, cell, out, flags_out=None):
         if pos4_r.shape[0] == 0:
             return
         p = pos4_r.numpy()
-        order = np.argsort(self._hash(p[:, :3], bmin, cell, n_global), kind="stable")
+        h = self._hash(p[:, :3], bmin, cell, n_global)
+        order = np.argsort(h, kind="stable")
         out.copy_(torch.from_numpy(p[order]))
+        if flags_out is not None:   # bit 0: bucket start, bit 1: cell change (first point of the segment: both)
+            hs = h[order]
+            cells = np.floor((p[order][:, :3] - bmin) / np.float32(cell)).astype(np.int32)
+            start = np.r_[True, hs[1:] != hs[:-1]]
+            newc = np.r_[True, np.any(cells[1:] != cells[:-1], axis=1)] | start
+            flags_out.copy_(torch.from_numpy((start.astype(np.uint8) | (newc.astype(np.uint8) << 1))))
 
     def new_grid_storage(self, n_global, dev):
         return None, torch.empty((n_global, 4), dtype=torch.float32)
 
-    def finish(self, ws, spos_full, n_global, bmin, cell):
-        return dict(spos=spos_full.numpy().copy(), bmin=bmin, cell=cell, n=n_global)
+    def finish(self, ws, spos_full, n_global, bmin, cell, flags_full=None):
+        sp = spos_full.numpy()
+        if flags_full is not None:   # the exchanged flags describe the globally sorted array
+            h = self._hash(np.ascontiguousarray(sp[:, :3]), bmin, cell, n_global)
+            assert np.array_equal((flags_full.numpy() & 1).astype(bool), np.r_[True, h[1:] != h[:-1]])
+        return dict(spos=sp.copy(), bmin=bmin, cell=cell, n=n_global)
 
 
 class OracleQueryOps(OracleOps):

@@ -117,18 +117,28 @@ def test_build_from_sorted_equals_build(cuda, gsx_lib):
     c = cuts.tolist()
     assert c[0] == 0 and c[-1] == n and all(c[i] <= c[i + 1] for i in range(world))
     assert sorted(pos4[:, 3].view(torch.int32).tolist()) == list(range(n))      # a permutation of the slab
-    ws2 = sor.workspace(n, cuda)
     off = lib.gsx_sor_spos_offset(n)
-    spos_full = ws2[off: off + n * 16].view(torch.float32).view(n, 4)
-    for o in range(world):                                                     # "owner o" sorts its range
-        m = c[o + 1] - c[o]
-        seg_in = pos4[c[o]: c[o + 1]].contiguous()
-        check(lib.gsx_sor_dist_merge(_ptr(seg_in), m, n, bminp, ref.cell, _ptr(spos_full[c[o]: c[o + 1]]), _ptr(ws),
-                                     ws.numel(), _stream()))
-    check(lib.gsx_sor_build_from_sorted(_ptr(spos_full), n, bminp, ref.cell, _ptr(ws2), ws2.numel(), _stream()))
-    grid2 = sor.SorGrid(n, ws2, ref.bmin, ref.cell)
-    for mode in ("i32wrap", "i64"):
-        a = sor.mean_dists(ref, 16, mode).cpu().numpy()
-        b = sor.mean_dists(grid2, 16, mode).cpu().numpy()
-        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
-        assert np.array_equal(a.view(np.uint32), oracle.sor_taichi_mean_dists(xyz_np, 16, mode).view(np.uint32))
+    want = {mode: oracle.sor_taichi_mean_dists(xyz_np, 16, mode) for mode in ("i32wrap", "i64")}
+    for with_flags in (False, True):   # stage C re-hashing every point / consuming the owners' per-point flags
+        ws2 = torch.empty(lib.gsx_sor_grid_workspace_bytes(n), dtype=torch.uint8, device=cuda)   # grid-only blob
+        spos_full = ws2[off: off + n * 16].view(torch.float32).view(n, 4)
+        flags = torch.zeros(n, dtype=torch.uint8, device=cuda) if with_flags else None
+        for o in range(world):                                                 # "owner o" sorts its range
+            m = c[o + 1] - c[o]
+            seg_in = pos4[c[o]: c[o + 1]].contiguous()
+            check(lib.gsx_sor_dist_merge(_ptr(seg_in), m, n, bminp, ref.cell, _ptr(spos_full[c[o]: c[o + 1]]),
+                                         _ptr(flags[c[o]: c[o + 1]]) if with_flags else None, _ptr(ws), ws.numel(),
+                                         _stream()))
+        check(lib.gsx_sor_build_from_sorted(_ptr(spos_full), _ptr(flags), n, bminp, ref.cell, _ptr(ws2), ws2.numel(),
+                                            _stream()))
+        grid2 = sor.SorGrid(n, ws2, ref.bmin, ref.cell)
+        for mode in ("i32wrap", "i64"):
+            a = sor.mean_dists(ref, 16, mode).cpu().numpy()
+            b = sor.mean_dists(grid2, 16, mode).cpu().numpy()
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (with_flags, mode)
+            assert np.array_equal(a.view(np.uint32), want[mode].view(np.uint32))
+            # cost-balanced sharding: 3 pretend ranks, batches dealt round-robin, union == the whole result
+            u = torch.zeros(n, dtype=torch.float32, device=cuda)
+            for r in range(3):
+                sor.mean_dists_strided(grid2, 16, mode, u, 3, r)
+            assert np.array_equal(u.cpu().numpy().view(np.uint32), a.view(np.uint32)), (with_flags, mode, "strided")
