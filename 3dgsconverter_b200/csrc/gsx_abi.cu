@@ -175,14 +175,15 @@ int gsx_sor_dist_local_run(const float* xyz_local_dev, int64_t n_local, int64_t 
                               (float4*)pos4_out_dev, (long long*)cuts_dev, w, (cudaStream_t)stream);
 }
 
-int gsx_sor_dist_merge(const float* pos4_dev, int64_t m, int64_t n_global, const float* bmin_host, float cell,
-                       float* pos4_sorted_dev, uint8_t* flags_sorted_dev, void* ws, int64_t ws_bytes, void* stream) {
+int gsx_sor_dist_merge(const float* pos4_dev, int64_t m, int64_t n_global, int64_t bucket_lo, int64_t bucket_hi,
+                       const float* bmin_host, float cell, float* pos4_sorted_dev, uint8_t* flags_sorted_dev, void* ws,
+                       int64_t ws_bytes, void* stream) {
     if (m == 0) return GSX_OK;
     SorWs w;
     int rc = carve_checked(ws, ws_bytes, m, w);
     if (rc) return rc;
-    return sor_dist_merge((const float4*)pos4_dev, m, n_global, bmin_host, cell, (float4*)pos4_sorted_dev,
-                          flags_sorted_dev, w, (cudaStream_t)stream);
+    return sor_dist_merge((const float4*)pos4_dev, m, n_global, bucket_lo, bucket_hi, bmin_host, cell,
+                          (float4*)pos4_sorted_dev, flags_sorted_dev, w, (cudaStream_t)stream);
 }
 
 int64_t gsx_sor_spos_offset(int64_t n) {

@@ -69,6 +69,7 @@ SorWs sor_carve(void* ws, int64_t ws_bytes, int64_t n, size_t sort_ws_bytes) {
     w.tab_box = c.take<float4>(2 * n);
     w.startbits = c.take<uint32_t>(nchunk);
     w.cellbits = c.take<uint32_t>(nchunk);
+    w.bigbits = c.take<uint32_t>(nchunk);
     w.caabb = c.take<float4>(2 * nchunk);
     w.saabb = c.take<float4>(2 * nsuper);
     w.partial = c.take<float>(6 * 1024);
@@ -413,8 +414,9 @@ __global__ void __launch_bounds__(256)
 // instead of every warp issuing the hash for one or two active lanes.
 __global__ void __launch_bounds__(1024)
     k_sor_finish_flags(const float4* __restrict__ spos, const uint8_t* __restrict__ flags, int64_t n, float bx, float by,
-                       float bz, float cell, uint64_t M64, int2* __restrict__ tab_se, uint32_t* __restrict__ startbits,
-                       uint32_t* __restrict__ cellbits, float4* __restrict__ caabb, float4* __restrict__ saabb) {
+                       float bz, float cell, uint64_t M64, int2* __restrict__ tab_se, float4* __restrict__ tab_box,
+                       uint32_t* __restrict__ startbits, uint32_t* __restrict__ cellbits, uint32_t* __restrict__ bigbits,
+                       float4* __restrict__ caabb, float4* __restrict__ saabb) {
     const int64_t j = (int64_t)blockIdx.x * 1024 + threadIdx.x;
     const int lane = lane_id();
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -458,13 +460,36 @@ __global__ void __launch_bounds__(1024)
         }
     }
     __syncthreads();
-    // hash only the boundary positions (compacted: ~64 per block)
+    // the boundary positions only (compacted: ~64 per block): hash, {start,end} entry, and -- one THREAD per bucket
+    // start -- the exact box of a small bucket by a serial walk over its (<= kSmallBucket, contiguous) points, scanning
+    // the start flags for its end.  Buckets that do not end within kSmallBucket points are left to k_sor_bucket_boxes
+    // (their start bit goes into bigbits).
     for (unsigned t = threadIdx.x; t < s_cnt; t += 1024) {
         const unsigned e = s_list[t];
         const int64_t pj = (int64_t)blockIdx.x * 1024 + (e >> 1);
         const float4 p = spos[pj];
         const uint32_t h = bucket_of(p.x, p.y, p.z, bx, by, bz, cell, n, M64);
-        if (e & 1u) tab_se[h].y = (int)(pj + 1); else tab_se[h].x = (int)pj;
+        if (e & 1u) {
+            tab_se[h].y = (int)(pj + 1);
+            continue;
+        }
+        tab_se[h].x = (int)pj;
+        float blo[3] = {p.x, p.y, p.z}, bhi[3] = {p.x, p.y, p.z};
+        int64_t u = pj + 1;
+        const int64_t lim = pj + kSmallBucket < n ? pj + kSmallBucket : n;
+        for (; u < lim; ++u) {
+            if (flags[u] & 1) break;
+            const float4 c = spos[u];
+            blo[0] = fminf(blo[0], c.x), blo[1] = fminf(blo[1], c.y), blo[2] = fminf(blo[2], c.z);
+            bhi[0] = fmaxf(bhi[0], c.x), bhi[1] = fmaxf(bhi[1], c.y), bhi[2] = fmaxf(bhi[2], c.z);
+        }
+        const bool closed = u == n || (u < n && (flags[u] & 1));
+        if (closed) {
+            tab_box[2 * (size_t)h] = make_float4(blo[0], blo[1], blo[2], 0.f);
+            tab_box[2 * (size_t)h + 1] = make_float4(bhi[0], bhi[1], bhi[2], 0.f);
+        } else {
+            atomicOr(bigbits + (pj >> 5), 1u << (pj & 31));
+        }
     }
     if (w == 0) {
         float v[6];
@@ -596,13 +621,16 @@ __global__ void __launch_bounds__(256) k_gather4(const float4* __restrict__ in, 
     if (j < n) out[j] = in[order[j]];
 }
 
+// sort key of the owner's points: the bucket RELATIVE to the first bucket of the owner's range (the high log2(G) bits
+// of the absolute bucket are constant inside a range: one radix pass less from 8 ranks on)
 __global__ void __launch_bounds__(256) k_sor_keys_pos4(const float4* __restrict__ pos4, int64_t n, int64_t n_global,
                                                        float bx, float by, float bz, float cell, uint64_t M64,
-                                                       uint64_t* __restrict__ keys, int32_t* __restrict__ vals) {
+                                                       uint64_t bucket_lo, uint64_t* __restrict__ keys,
+                                                       int32_t* __restrict__ vals) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 p = pos4[i];
-    keys[i] = bucket_key(p.x, p.y, p.z, bx, by, bz, cell, n_global, M64);
+    keys[i] = bucket_key(p.x, p.y, p.z, bx, by, bz, cell, n_global, M64) - (bucket_lo << kMortonBits);
     vals[i] = (int32_t)i;
 }
 
@@ -633,18 +661,20 @@ __global__ void __launch_bounds__(256)
     flags[j] = (uint8_t)((start ? 1 : 0) | ((newcell || start) ? 2 : 0));
 }
 
-int sor_dist_merge(const float4* pos4_in, int64_t m, int64_t n_global, const float* bmin, float cell, float4* pos4_out,
-                   uint8_t* flags_out, SorWs& w, cudaStream_t st) {
+int sor_dist_merge(const float4* pos4_in, int64_t m, int64_t n_global, int64_t bucket_lo, int64_t bucket_hi,
+                   const float* bmin, float cell, float4* pos4_out, uint8_t* flags_out, SorWs& w, cudaStream_t st) {
     GSX_NVTX("gsx::sor_dist_merge");
     if (m == 0) return GSX_OK;
+    GSX_REQUIRE(bucket_lo >= 0 && bucket_lo < bucket_hi && bucket_hi <= n_global, GSX_ERR_ARG, "sor: bad bucket range");
     int blocks = (int)((m + 255) / 256);
     k_sor_keys_pos4<<<blocks, 256, 0, st>>>(pos4_in, m, n_global, bmin[0], bmin[1], bmin[2], cell,
-                                            0xFFFFFFFFFFFFFFFFull / (uint64_t)n_global, w.keys0, w.vals0);
+                                            0xFFFFFFFFFFFFFFFFull / (uint64_t)n_global, (uint64_t)bucket_lo, w.keys0,
+                                            w.vals0);
     GSX_KERNEL_CHECK();
     uint64_t* ks = nullptr;
     int32_t* order = nullptr;
-    int rc = radix_sort_pairs(w.keys0, w.keys1, w.vals0, w.vals1, m, 0, kMortonBits + hash_bits_of(n_global), w.sort_ws,
-                              w.sort_ws_bytes, &ks, &order, st);
+    int rc = radix_sort_pairs(w.keys0, w.keys1, w.vals0, w.vals1, m, 0, kMortonBits + hash_bits_of(bucket_hi - bucket_lo),
+                              w.sort_ws, w.sort_ws_bytes, &ks, &order, st);
     if (rc) return rc;
     if (flags_out)
         k_owner_gather_flags<<<blocks, 256, 0, st>>>(pos4_in, order, ks, m, bmin[0], bmin[1], bmin[2], cell, pos4_out,
@@ -666,10 +696,13 @@ int sor_build_from_sorted(const float4* spos_in, const uint8_t* flags, int64_t n
     if (!flags) return sor_finish<false>(nullptr, n, bmin, cell, w, st);
     const uint64_t M64 = 0xFFFFFFFFFFFFFFFFull / (uint64_t)n;
     GSX_CUDA_CHECK(cudaMemsetAsync(w.tab_se, 0, (size_t)n * sizeof(int2), st));
+    GSX_CUDA_CHECK(cudaMemsetAsync(w.bigbits, 0, (size_t)((n + 31) / 32) * sizeof(uint32_t), st));
     k_sor_finish_flags<<<(int)((n + 1023) / 1024), 1024, 0, st>>>(w.spos, flags, n, bmin[0], bmin[1], bmin[2], cell, M64,
-                                                                  w.tab_se, w.startbits, w.cellbits, w.caabb, w.saabb);
+                                                                  w.tab_se, w.tab_box, w.startbits, w.cellbits, w.bigbits,
+                                                                  w.caabb, w.saabb);
     GSX_KERNEL_CHECK();
-    k_sor_bucket_boxes<<<(int)((n + 255) / 256), 256, 0, st>>>(w.startbits, w.spos, w.caabb, w.tab_se, n, bmin[0],
+    // only the buckets longer than kSmallBucket are left (their chunks' boxes are complete now)
+    k_sor_bucket_boxes<<<(int)((n + 255) / 256), 256, 0, st>>>(w.bigbits, w.spos, w.caabb, w.tab_se, n, bmin[0],
                                                                bmin[1], bmin[2], cell, M64, w.tab_box);
     GSX_KERNEL_CHECK();
     return GSX_OK;

@@ -16,6 +16,7 @@ struct SorWs {
     float4* tab_box;      // per bucket {lo.xyz,-},{hi.xyz,-}: exact box of its points (occupied buckets only)
     uint32_t* startbits;  // one bit per sorted position: starts a bucket
     uint32_t* cellbits;   // one bit per sorted position: other grid cell than the position before
+    uint32_t* bigbits;    // one bit per sorted position: starts a bucket longer than kSmallBucket (distributed stage C)
     float4* caabb;  // 2 float4 per 32-point chunk: {lo.x,lo.y,lo.z,hi.x},{hi.y,hi.z,-,-}
     float4* saabb;  // same per 1024-point super
     float* partial;
@@ -44,8 +45,8 @@ int sor_mean_dists(SorWs& w, int64_t q_begin, int64_t q_end, int q_stride, int q
 int sor_dist_local_run(const float* xyz, int64_t n_local, int64_t idx_base, int64_t n_global, int world,
                        const float* bmin, float cell, float4* pos4_out, long long* cuts_dev, SorWs& w,
                        cudaStream_t st);
-int sor_dist_merge(const float4* pos4_in, int64_t m, int64_t n_global, const float* bmin, float cell, float4* pos4_out,
-                   uint8_t* flags_out, SorWs& w, cudaStream_t st);
+int sor_dist_merge(const float4* pos4_in, int64_t m, int64_t n_global, int64_t bucket_lo, int64_t bucket_hi,
+                   const float* bmin, float cell, float4* pos4_out, uint8_t* flags_out, SorWs& w, cudaStream_t st);
 int sor_build_from_sorted(const float4* spos_in, const uint8_t* flags, int64_t n, const float* bmin, float cell, SorWs& w,
                           cudaStream_t st);
 

@@ -73,11 +73,38 @@ __device__ __forceinline__ float elem(const float* __restrict__ a, int64_t i, fl
     return v;
 }
 
+// One leaf = 8 consecutive lanes: lane j IS NumPy's accumulator r[j] (elements j, j+8, j+16, ... of the leaf), so the
+// 8 lanes read one 32-byte sector per step; the combine ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) is a 3-step xor butterfly
+// (float addition is commutative, so both lanes of a pair compute the same bits); lane 0 adds the serial tail.
+template <bool SQ, class Get>
+__device__ __forceinline__ float leaf_sum8(int64_t off, int64_t m, int j, Get get) {
+    const unsigned grp = 0xffu << ((threadIdx.x & 31) & ~7);
+    float res;
+    if (m < 8) {
+        res = 0.f;
+        if (j == 0)
+            for (int64_t i = 0; i < m; ++i) res = __fadd_rn(res, get(off + i));
+        return res;
+    }
+    float r = get(off + j);
+    const int64_t body = m - (m % 8);
+    for (int64_t i = 8; i < body; i += 8) r = __fadd_rn(r, get(off + i + j));
+    r = __fadd_rn(r, __shfl_xor_sync(grp, r, 1));
+    r = __fadd_rn(r, __shfl_xor_sync(grp, r, 2));
+    r = __fadd_rn(r, __shfl_xor_sync(grp, r, 4));
+    res = r;
+    if (j == 0)
+        for (int64_t i = body; i < m; ++i) res = __fadd_rn(res, get(off + i));
+    return res;
+}
+
 template <bool SQ>
 __global__ void __launch_bounds__(128) k_pw_leaves(const float* __restrict__ a, int64_t n, int dmax,
                                                    const float* __restrict__ meanp, float* __restrict__ slot) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (1u << dmax)) return;
+    const uint64_t gt = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t t = (uint32_t)(gt >> 3);
+    const int j = (int)(gt & 7);
+    if (t >= (1u << dmax)) return;   // (a whole group of 8 leaves together: the shuffles below stay converged)
     int64_t off, m;
     int reached;
     bool full = walk(n, dmax, t, off, m, reached);
@@ -86,24 +113,8 @@ __global__ void __launch_bounds__(128) k_pw_leaves(const float* __restrict__ a, 
         if (t & ((1u << (dmax - reached)) - 1u)) return;
     }
     const float mean = SQ ? meanp[0] : 0.f;
-    float res;
-    if (m < 8) {
-        res = 0.f;
-        for (int64_t i = 0; i < m; ++i) res = __fadd_rn(res, elem<SQ>(a, off + i, mean));
-    } else {
-        float r[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = elem<SQ>(a, off + j, mean);
-        int64_t i;
-        for (i = 8; i < m - (m % 8); i += 8) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], elem<SQ>(a, off + i + j, mean));
-        }
-        res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
-                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
-        for (; i < m; ++i) res = __fadd_rn(res, elem<SQ>(a, off + i, mean));
-    }
-    slot[t] = res;
+    const float res = leaf_sum8<SQ>(off, m, j, [&](int64_t i) { return elem<SQ>(a, i, mean); });
+    if (j == 0) slot[t] = res;
 }
 
 // combine the nodes of depth d: node u = left(u) + right(u), in place at the left child's slot
@@ -139,7 +150,7 @@ __global__ void __launch_bounds__(1024) k_pw_top(int64_t n, int dmax, int dtop, 
 template <bool SQ>
 static int pairwise_pass(const float* a, int64_t n, int dmax, float* slot, float* out, cudaStream_t st) {
     uint32_t leaves = 1u << dmax;
-    k_pw_leaves<SQ><<<(leaves + 127) / 128, 128, 0, st>>>(a, n, dmax, out, slot);
+    k_pw_leaves<SQ><<<(unsigned)(((uint64_t)leaves * 8 + 127) / 128), 128, 0, st>>>(a, n, dmax, out, slot);
     GSX_KERNEL_CHECK();
     int d = dmax - 1;
     for (; d > 9; --d) {
@@ -176,7 +187,9 @@ __global__ void __launch_bounds__(128)
     k_pw_leaves_dist(const float* __restrict__ a_local, int64_t base, int64_t n_local, int64_t n, int dmax,
                      const float* __restrict__ meanp, const float* __restrict__ halo,
                      const long long* __restrict__ bases, int world, float* __restrict__ slot) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t gt = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t t = (uint32_t)(gt >> 3);
+    const int j = (int)(gt & 7);
     if (t >= (1u << dmax)) return;
     int64_t off, m;
     int reached;
@@ -184,12 +197,12 @@ __global__ void __launch_bounds__(128)
     if (!full && (t & ((1u << (dmax - reached)) - 1u))) return;
     if (off < base || off >= base + n_local) return;  // another rank owns this leaf
     const float mean = SQ ? meanp[0] : 0.f;
-    int hr = 0;  // slab that holds the spill-over elements (advances monotonically)
     auto get = [&](int64_t i) -> float {
         float v;
         if (i < base + n_local) {
             v = a_local[i - base];
-        } else {
+        } else {   // spill-over into the following slab(s): the first 128 elements of every slab are in `halo`
+            int hr = 0;
             while (hr + 1 < world && i >= bases[hr + 1]) ++hr;
             v = halo[(size_t)hr * 128 + (i - bases[hr])];
         }
@@ -199,24 +212,8 @@ __global__ void __launch_bounds__(128)
         }
         return v;
     };
-    float res;
-    if (m < 8) {
-        res = 0.f;
-        for (int64_t i = 0; i < m; ++i) res = __fadd_rn(res, get(off + i));
-    } else {
-        float r[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) r[j] = get(off + j);
-        int64_t i;
-        for (i = 8; i < m - (m % 8); i += 8) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], get(off + i + j));
-        }
-        res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
-                        __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
-        for (; i < m; ++i) res = __fadd_rn(res, get(off + i));
-    }
-    slot[t] = res;
+    const float res = leaf_sum8<SQ>(off, m, j, get);
+    if (j == 0) slot[t] = res;
 }
 
 int64_t pairwise_slots(int64_t n) {
@@ -232,8 +229,9 @@ int pairwise_leaves_dist(const float* a_local, int64_t base, int64_t n_local, in
     uint32_t leaves = 1u << dmax;
     GSX_CUDA_CHECK(cudaMemsetAsync(slot, 0, (size_t)leaves * sizeof(float), st));
     if (n_local == 0) return GSX_OK;
-    if (sq) k_pw_leaves_dist<true><<<(leaves + 127) / 128, 128, 0, st>>>(a_local, base, n_local, n, dmax, meanstd, halo, bases_dev, world, slot);
-    else k_pw_leaves_dist<false><<<(leaves + 127) / 128, 128, 0, st>>>(a_local, base, n_local, n, dmax, meanstd, halo, bases_dev, world, slot);
+    const unsigned lb = (unsigned)(((uint64_t)leaves * 8 + 127) / 128);
+    if (sq) k_pw_leaves_dist<true><<<lb, 128, 0, st>>>(a_local, base, n_local, n, dmax, meanstd, halo, bases_dev, world, slot);
+    else k_pw_leaves_dist<false><<<lb, 128, 0, st>>>(a_local, base, n_local, n, dmax, meanstd, halo, bases_dev, world, slot);
     GSX_KERNEL_CHECK();
     return GSX_OK;
 }

@@ -40,7 +40,7 @@ _SIGS = {
     "gsx_sor_cell_size": (C.c_float, [_f32p, _i64]),
     "gsx_sor_build": (C.c_int, [_vp, _i64, _f32p, C.c_float, _vp, _i64, _vp]),
     "gsx_sor_dist_local_run": (C.c_int, [_vp, _i64, _i64, _i64, _i32, _f32p, C.c_float, _vp, _vp, _vp, _i64, _vp]),
-    "gsx_sor_dist_merge": (C.c_int, [_vp, _i64, _i64, _f32p, C.c_float, _vp, _vp, _vp, _i64, _vp]),
+    "gsx_sor_dist_merge": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _f32p, C.c_float, _vp, _vp, _vp, _i64, _vp]),
     "gsx_sor_spos_offset": (_i64, [_i64]),
     "gsx_sor_build_from_sorted": (C.c_int, [_vp, _vp, _i64, _f32p, C.c_float, _vp, _i64, _vp]),
     "gsx_sor_mean_dists": (C.c_int, [_i64, _i32, _i32, _f32p, C.c_float, _vp, _i64, _vp, _vp, _vp]),

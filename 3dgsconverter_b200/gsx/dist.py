@@ -143,7 +143,7 @@ class _GsxSorOps:
                                          _ptr(ws_l), ws_l.numel(), _stream()), "gsx_sor_dist_local_run")
         return pos4, cuts
 
-    def merge_into(self, pos4_r, n_global, bmin, cell, out, flags_out=None):
+    def merge_into(self, pos4_r, n_global, bmin, cell, out, flags_out=None, bucket_range=None):
         """B: sort the received points of this rank's bucket range by (bucket, in-cell Morton) into `out`; with
         `flags_out` (uint8 per point) also the bucket-start / cell-change flags stage C consumes."""
         import ctypes as C
@@ -154,9 +154,10 @@ class _GsxSorOps:
         if m == 0:
             return
         ws_m = sor.workspace(m, pos4_r.device)
-        check(lib.gsx_sor_dist_merge(_ptr(pos4_r), m, n_global, bmin.ctypes.data_as(C.POINTER(C.c_float)), cell,
-                                     _ptr(out), _ptr(flags_out), _ptr(ws_m), ws_m.numel(), _stream()),
-              "gsx_sor_dist_merge")
+        lo, hi = bucket_range if bucket_range is not None else (0, n_global)
+        check(lib.gsx_sor_dist_merge(_ptr(pos4_r), m, n_global, int(lo), int(hi),
+                                     bmin.ctypes.data_as(C.POINTER(C.c_float)), cell, _ptr(out), _ptr(flags_out), _ptr(ws_m),
+                                     ws_m.numel(), _stream()), "gsx_sor_dist_merge")
 
     def new_grid_storage(self, n_global, dev):
         """Workspace of the final grid and a [n_global,4] view of its sorted-position array (exchange target)."""
@@ -316,7 +317,9 @@ def build_grid_distributed(xyz_local: torch.Tensor, group=None, ops=None, stamps
     # 4. B: owner sort straight into the slot, then the ragged all-gather of the slots
     ws, spos_full = ops.new_grid_storage(n_global, dev)
     flags_full = torch.empty(n_global, dtype=torch.uint8, device=dev)   # bit 0 bucket start, bit 1 cell change
-    ops.merge_into(pos4_r, n_global, bmin, cell, spos_full[seg_base: seg_base + m], flags_full[seg_base: seg_base + m])
+    ob = _owner_bounds(n_global, world)
+    ops.merge_into(pos4_r, n_global, bmin, cell, spos_full[seg_base: seg_base + m], flags_full[seg_base: seg_base + m],
+                   bucket_range=(ob[rank], ob[rank + 1]))
     st.mark("build_B_owner_sort")
     exchange_segments([spos_full, flags_full], seg_sizes, rank, group)
     st.mark("nccl_segments")

@@ -68,7 +68,7 @@ int gsx_sor_build(const float* xyz_dev, int64_t n, const float* bmin_host, float
  *  A. local_run:  stable partition of the slab by bucket owner (one radix pass); outputs float4
  *     {x,y,z, bits(idx_base + local index)} grouped by owner and cuts_dev[G+1] = first position of every owner
  *     -> the caller exchanges the groups (all-to-all).
- *  B. merge:      sorts the m received points of this rank's bucket range by (bucket, in-cell Morton)
+ *  B. merge:      sorts the m received points of this rank's bucket range [bucket_lo, bucket_hi) by (bucket, in-cell Morton)
  *     -> the caller all-gathers the segments in owner order = the globally hash-sorted array.  With flags_sorted_dev
  *     the owner also emits one byte per sorted point (bit 0: starts a bucket, bit 1: other grid cell than the point
  *     before) -- exchanged along with the segment (1 B/pt next to 16 B/pt), it spares every receiving rank the
@@ -81,9 +81,9 @@ int gsx_sor_build(const float* xyz_dev, int64_t n, const float* bmin_host, float
 int gsx_sor_dist_local_run(const float* xyz_local_dev, int64_t n_local, int64_t idx_base, int64_t n_global,
                            int32_t world, const float* bmin_host, float cell, float* pos4_out_dev,
                            int64_t* cuts_dev, void* ws, int64_t ws_bytes, void* stream);
-int gsx_sor_dist_merge(const float* pos4_dev, int64_t m, int64_t n_global, const float* bmin_host, float cell,
-                       float* pos4_sorted_dev, uint8_t* flags_sorted_dev /* uint8[m] or NULL */, void* ws,
-                       int64_t ws_bytes, void* stream);
+int gsx_sor_dist_merge(const float* pos4_dev, int64_t m, int64_t n_global, int64_t bucket_lo, int64_t bucket_hi,
+                       const float* bmin_host, float cell, float* pos4_sorted_dev,
+                       uint8_t* flags_sorted_dev /* uint8[m] or NULL */, void* ws, int64_t ws_bytes, void* stream);
 int64_t gsx_sor_spos_offset(int64_t n);
 int gsx_sor_build_from_sorted(const float* spos4_dev, const uint8_t* flags_dev /* uint8[n] or NULL */, int64_t n,
                               const float* bmin_host, float cell, void* ws, int64_t ws_bytes, void* stream);

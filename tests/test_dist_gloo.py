@@ -271,11 +271,13 @@ class OracleBuildOps:
         cuts = np.searchsorted(owner[order], np.arange(world + 1))
         return torch.from_numpy(pos4), torch.from_numpy(cuts.astype(np.int64))
 
-    def merge_into(self, pos4_r, n_global, bmin, cell, out, flags_out=None):
+    def merge_into(self, pos4_r, n_global, bmin, cell, out, flags_out=None, bucket_range=None):
         if pos4_r.shape[0] == 0:
             return
         p = pos4_r.numpy()
         h = self._hash(p[:, :3], bmin, cell, n_global)
+        if bucket_range is not None:
+            assert np.all((h >= bucket_range[0]) & (h < bucket_range[1]))     # only the owner's buckets arrive
         order = np.argsort(h, kind="stable")
         out.copy_(torch.from_numpy(p[order]))
         if flags_out is not None:   # bit 0: bucket start, bit 1: cell change (first point of the segment: both)

@@ -126,7 +126,8 @@ def test_build_from_sorted_equals_build(cuda, gsx_lib):
         for o in range(world):                                                 # "owner o" sorts its range
             m = c[o + 1] - c[o]
             seg_in = pos4[c[o]: c[o + 1]].contiguous()
-            check(lib.gsx_sor_dist_merge(_ptr(seg_in), m, n, bminp, ref.cell, _ptr(spos_full[c[o]: c[o + 1]]),
+            blo, bhi = (o * n + world - 1) // world, ((o + 1) * n + world - 1) // world   # owner o's bucket range
+            check(lib.gsx_sor_dist_merge(_ptr(seg_in), m, n, blo, bhi, bminp, ref.cell, _ptr(spos_full[c[o]: c[o + 1]]),
                                          _ptr(flags[c[o]: c[o + 1]]) if with_flags else None, _ptr(ws), ws.numel(),
                                          _stream()))
         check(lib.gsx_sor_build_from_sorted(_ptr(spos_full), _ptr(flags), n, bminp, ref.cell, _ptr(ws2), ws2.numel(),
