@@ -140,6 +140,85 @@ __global__ void __launch_bounds__(256) k_vox_count_grid_agg(const float* __restr
         if (sval[t] > 0) commit(skey[t], sval[t]);
 }
 
+// Small voxel boxes (<= kSmemCells cells: --density_sensitivity 0.5 over a 24-unit cloud is 22^3 = 10.6 k): the whole
+// histogram lives in shared memory.  Persistent CTAs count a contiguous slice of the cloud with shared-memory atomics
+// (4 splats = three 128-bit streaming loads per thread) and flush their non-zero bins with ONE global atomicAdd each:
+// <= cells per CTA instead of one same-address global atomic per splat (clustered clouds put 10^5..10^6 splats into a
+// handful of voxels).  thr > 0: also the dense-voxel detection of the one-shot path (the CTA whose add crosses thr).
+constexpr int kSmemCells = 24 * 1024;
+__global__ void __launch_bounds__(512)
+    k_vox_count_smem(const float* __restrict__ xyz, int64_t n, float voxel, VoxGrid g, int ncell, int thr,
+                     int* __restrict__ grid, unsigned long long* __restrict__ counters,
+                     long long* __restrict__ dense_vox, int64_t cap, unsigned long long* __restrict__ oob) {
+    extern __shared__ int sh_hist[];
+    for (int t = threadIdx.x; t < ncell; t += blockDim.x) sh_hist[t] = 0;
+    __syncthreads();
+    const int64_t n4 = n / 4;                       // groups of 4 splats = 3 float4
+    const int64_t per = (n4 + gridDim.x - 1) / gridDim.x;
+    const int64_t g0 = (int64_t)blockIdx.x * per, g1 = g0 + per < n4 ? g0 + per : n4;
+    const bool vec = (reinterpret_cast<uintptr_t>(xyz) & 15) == 0;
+    unsigned long long bad = 0;
+    auto add = [&](float x, float y, float z) {
+        const long long rx = voxel_of(x, voxel) - g.q0[0], ry = voxel_of(y, voxel) - g.q0[1], rz = voxel_of(z, voxel) - g.q0[2];
+        if (rx < 0 || ry < 0 || rz < 0 || rx >= g.dim[0] || ry >= g.dim[1] || rz >= g.dim[2]) {
+            ++bad;
+            return;
+        }
+        atomicAdd(&sh_hist[(int)((rx * g.dim[1] + ry) * g.dim[2] + rz)], 1);
+    };
+    for (int64_t t = g0 + threadIdx.x; t < g1; t += blockDim.x) {
+        if (vec) {
+            const float4* p4 = reinterpret_cast<const float4*>(xyz) + 3 * t;
+            const float4 a = ld_stream_f4(p4), b = ld_stream_f4(p4 + 1), c = ld_stream_f4(p4 + 2);
+            add(a.x, a.y, a.z);
+            add(a.w, b.x, b.y);
+            add(b.z, b.w, c.x);
+            add(c.y, c.z, c.w);
+        } else {
+            for (int e = 0; e < 4; ++e) add(xyz[12 * t + 3 * e], xyz[12 * t + 3 * e + 1], xyz[12 * t + 3 * e + 2]);
+        }
+    }
+    if (blockIdx.x == 0)   // ragged tail (< 4 splats)
+        for (int64_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) add(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    if (bad && oob) atomicAdd(oob, bad);
+    __syncthreads();
+    for (int t = threadIdx.x; t < ncell; t += blockDim.x) {
+        const int c = sh_hist[t];
+        if (c == 0) continue;
+        const int old = atomicAdd(grid + t, c);
+        if (thr > 0) {
+            if (old == 0) atomicAdd(counters + 1, 1ull);
+            if (old < thr && old + c >= thr) {
+                const unsigned long long slot = atomicAdd(counters, 1ull);
+                if ((int64_t)slot < cap) {
+                    const long long cz = t % g.dim[2], cy = (t / g.dim[2]) % g.dim[1], cx = t / (g.dim[2] * g.dim[1]);
+                    dense_vox[3 * slot] = cx + g.q0[0];
+                    dense_vox[3 * slot + 1] = cy + g.q0[1];
+                    dense_vox[3 * slot + 2] = cz + g.q0[2];
+                }
+            }
+        }
+    }
+}
+
+static int launch_vox_count_smem(const float* xyz, int64_t n, float voxel, const VoxGrid& g, size_t ncell, int thr, int* grid,
+                                 unsigned long long* counters, long long* dvox, int64_t cap, unsigned long long* oob,
+                                 cudaStream_t st) {
+    const size_t smem = ncell * sizeof(int);
+    static bool attr_done = false;
+    if (!attr_done) {
+        GSX_CUDA_CHECK(cudaFuncSetAttribute(k_vox_count_smem, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(kSmemCells * sizeof(int))));
+        attr_done = true;
+    }
+    int blocks = sm_count() * 2;
+    const int64_t n4 = n / 4;
+    if ((int64_t)blocks > (n4 + 511) / 512) blocks = (int)((n4 + 511) / 512);
+    if (blocks < 1) blocks = 1;
+    k_vox_count_smem<<<blocks, 512, smem, st>>>(xyz, n, voxel, g, (int)ncell, thr, grid, counters, dvox, cap, oob);
+    return GSX_OK;
+}
+
 __global__ void k_vox_dense_counts_grid(const long long* __restrict__ dense_vox, int64_t nd, VoxGrid g,
                                         const int* __restrict__ grid, int* __restrict__ dense_cnt) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -319,7 +398,10 @@ int density_voxel_count(const float* xyz, int64_t n, float voxel, int64_t min_po
     if (use_grid) {
         size_t ncell = (size_t)g.dim[0] * g.dim[1] * g.dim[2];
         GSX_CUDA_CHECK(cudaMemsetAsync(blob, 0, ncell * 4, st));
-        if (ncell < 0xfffffff0ull) {
+        if (ncell <= (size_t)kSmemCells) {
+            int rc2 = launch_vox_count_smem(xyz, n, voxel, g, ncell, thr, (int*)blob, counters, dvox, cap, nullptr, st);
+            if (rc2) return rc2;
+        } else if (ncell < 0xfffffff0ull) {
             int ablocks = (int)((n + 256 * kAggItems - 1) / (256 * kAggItems));
             k_vox_count_grid_agg<<<ablocks, 256, 0, st>>>(xyz, n, voxel, g, thr, (int*)blob, counters, dvox, cap);
         } else {
@@ -434,7 +516,12 @@ int density_grid_count(const float* xyz, int64_t n, float voxel, const int64_t* 
     size_t ncell;
     int rc = make_grid(q0, dim, g, ncell);
     if (rc) return rc;
-    k_vox_count_grid_only<<<(int)((n + 255) / 256), 256, 0, st>>>(xyz, n, voxel, g, grid_dev, oob_dev);
+    if (ncell <= (size_t)kSmemCells) {
+        rc = launch_vox_count_smem(xyz, n, voxel, g, ncell, 0, grid_dev, nullptr, nullptr, 0, oob_dev, st);
+        if (rc) return rc;
+    } else {
+        k_vox_count_grid_only<<<(int)((n + 255) / 256), 256, 0, st>>>(xyz, n, voxel, g, grid_dev, oob_dev);
+    }
     GSX_KERNEL_CHECK();
     return GSX_OK;
 }

@@ -70,6 +70,7 @@ SorWs sor_carve(void* ws, int64_t ws_bytes, int64_t n, size_t sort_ws_bytes) {
     w.startbits = c.take<uint32_t>(nchunk);
     w.cellbits = c.take<uint32_t>(nchunk);
     w.bigbits = c.take<uint32_t>(nchunk);
+    w.startlist = c.take<uint32_t>(n / 8 + 1024);
     w.caabb = c.take<float4>(2 * nchunk);
     w.saabb = c.take<float4>(2 * nsuper);
     w.partial = c.take<float>(6 * 1024);
@@ -250,7 +251,8 @@ __global__ void __launch_bounds__(1024)
     k_sor_finish(const float* __restrict__ xyz, const int32_t* __restrict__ order, const uint64_t* __restrict__ keys,
                  float4* __restrict__ spos, int64_t n, float bx, float by, float bz, float cell, uint64_t M64,
                  int2* __restrict__ tab_se, uint32_t* __restrict__ startbits, uint32_t* __restrict__ cellbits,
-                 float4* __restrict__ caabb, float4* __restrict__ saabb) {
+                 float4* __restrict__ caabb, float4* __restrict__ saabb, const unsigned int* __restrict__ gate) {
+    if (gate && !*gate) return;   // fallback of the flag path: runs only when its start list overflowed
     const int64_t j = (int64_t)blockIdx.x * 1024 + threadIdx.x;
     const int lane = lane_id();
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -352,7 +354,9 @@ __global__ void __launch_bounds__(1024)
 __global__ void __launch_bounds__(256)
     k_sor_bucket_boxes(const uint32_t* __restrict__ startbits, const float4* __restrict__ spos,
                        const float4* __restrict__ caabb, const int2* __restrict__ tab_se, int64_t n, float bx,
-                       float by, float bz, float cell, uint64_t M64, float4* __restrict__ tab_box) {
+                       float by, float bz, float cell, uint64_t M64, float4* __restrict__ tab_box,
+                       const unsigned int* __restrict__ gate) {
+    if (gate && !*gate) return;
     const int lane = lane_id();
     const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (chunk * 32 >= n) return;
@@ -408,19 +412,35 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// Stage C when the owners shipped per-point flags (bit 0 bucket start, bit 1 cell change): a pure streaming pass --
-// chunk / super boxes, the two bit masks, and the {start,end} table entries.  Only bucket boundaries need the hash;
-// they are ~1 in 32 positions, so they are compacted through shared memory and hashed by as few warps as possible
-// instead of every warp issuing the hash for one or two active lanes.
+// Stage C when the owners shipped per-point flags (bit 0 bucket start, bit 1 cell change).  Three kernels, none of
+// which hashes every point (the replicated re-hash was ~130 of ~250 instructions per point) and none of which leaves
+// a block waiting on a serial tail:
+//   k_sor_finish_flags  one pass over the sorted order: chunk / super boxes, the start and cell bit masks, and the
+//                       positions of the bucket starts compacted into ONE global list (a block reserves its slice
+//                       with a single atomicAdd);
+//   k_sor_bucket_tail   one THREAD per listed bucket start (perfectly compacted, ~1/32 of the points): hash of that
+//                       one point, then a serial walk over the bucket's contiguous points (scanning the start flags
+//                       for its end) -> {start,end} entry and the exact box of every bucket of <= kSmallBucket points;
+//                       longer buckets only get their start written and a bit in `bigbits`;
+//   k_sor_big_buckets   one warp per 32 positions, only for the few long buckets: end found by scanning the start
+//                       bit mask, box from the chunk boxes (complete after the first kernel).
+// The list has room for n/8 + 1024 starts (average bucket >= 8 points); if it overflows, a device-side flag makes
+// the last two kernels return and the re-hashing kernels (k_sor_finish<false>, k_sor_bucket_boxes) take over --
+// no host round trip either way.
+struct StartList {
+    unsigned int* count;      // [0] entries reserved, [1] overflow flag
+    unsigned int* pos;        // start positions
+    unsigned int capacity;
+};
+
 __global__ void __launch_bounds__(1024)
-    k_sor_finish_flags(const float4* __restrict__ spos, const uint8_t* __restrict__ flags, int64_t n, float bx, float by,
-                       float bz, float cell, uint64_t M64, int2* __restrict__ tab_se, float4* __restrict__ tab_box,
-                       uint32_t* __restrict__ startbits, uint32_t* __restrict__ cellbits, uint32_t* __restrict__ bigbits,
-                       float4* __restrict__ caabb, float4* __restrict__ saabb) {
+    k_sor_finish_flags(const float4* __restrict__ spos, const uint8_t* __restrict__ flags, int64_t n,
+                       uint32_t* __restrict__ startbits, uint32_t* __restrict__ cellbits, float4* __restrict__ caabb,
+                       float4* __restrict__ saabb, StartList sl) {
     const int64_t j = (int64_t)blockIdx.x * 1024 + threadIdx.x;
     const int lane = lane_id();
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    bool start = false, end = false, newcell = false;
+    bool start = false, newcell = false;
     if (j < n) {
         const float4 p = spos[j];
         lo[0] = hi[0] = p.x;
@@ -429,23 +449,17 @@ __global__ void __launch_bounds__(1024)
         const uint8_t f = flags[j];
         start = (f & 1) != 0;
         newcell = (f & 2) != 0;
-        end = j == n - 1 || (flags[j + 1] & 1) != 0;
     }
     const unsigned sb = __ballot_sync(GSX_FULL, start), cb = __ballot_sync(GSX_FULL, newcell);
-    // boundary list of this block: entries = position << 1 | is_end
-    __shared__ unsigned s_cnt;
-    __shared__ unsigned s_list[2048];
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
-    if (start) s_list[atomicAdd(&s_cnt, 1u)] = (unsigned)threadIdx.x << 1;
-    if (end) s_list[atomicAdd(&s_cnt, 1u)] = ((unsigned)threadIdx.x << 1) | 1u;
+    __shared__ unsigned s_wcnt[32], s_base;
+    const int w = threadIdx.x >> 5;
+    if (lane == 0) s_wcnt[w] = __popc(sb);
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
         lo[a] = ord_to_float(__reduce_min_sync(GSX_FULL, float_to_ord(lo[a])));
         hi[a] = ord_to_float(__reduce_max_sync(GSX_FULL, float_to_ord(hi[a])));
     }
     __shared__ float sm[6][32];
-    const int w = threadIdx.x >> 5;
     const int64_t chunk = (int64_t)blockIdx.x * 32 + w;
     if (lane == 0) {
         if (chunk * 32 < n) {
@@ -460,66 +474,160 @@ __global__ void __launch_bounds__(1024)
         }
     }
     __syncthreads();
-    // the boundary positions only (compacted: ~64 per block): hash, {start,end} entry, and -- one THREAD per bucket
-    // start -- the exact box of a small bucket by a serial walk over its (<= kSmallBucket, contiguous) points, scanning
-    // the start flags for its end.  Buckets that do not end within kSmallBucket points are left to k_sor_bucket_boxes
-    // (their start bit goes into bigbits).
-    for (unsigned t = threadIdx.x; t < s_cnt; t += 1024) {
-        const unsigned e = s_list[t];
-        const int64_t pj = (int64_t)blockIdx.x * 1024 + (e >> 1);
-        const float4 p = spos[pj];
-        const uint32_t h = bucket_of(p.x, p.y, p.z, bx, by, bz, cell, n, M64);
-        if (e & 1u) {
-            tab_se[h].y = (int)(pj + 1);
-            continue;
-        }
-        tab_se[h].x = (int)pj;
-        float blo[3] = {p.x, p.y, p.z}, bhi[3] = {p.x, p.y, p.z};
-        int64_t u = pj + 1;
-        const int64_t lim = pj + kSmallBucket < n ? pj + kSmallBucket : n;
-        for (; u < lim; ++u) {
-            if (flags[u] & 1) break;
-            const float4 c = spos[u];
-            blo[0] = fminf(blo[0], c.x), blo[1] = fminf(blo[1], c.y), blo[2] = fminf(blo[2], c.z);
-            bhi[0] = fmaxf(bhi[0], c.x), bhi[1] = fmaxf(bhi[1], c.y), bhi[2] = fmaxf(bhi[2], c.z);
-        }
-        const bool closed = u == n || (u < n && (flags[u] & 1));
-        if (closed) {
-            tab_box[2 * (size_t)h] = make_float4(blo[0], blo[1], blo[2], 0.f);
-            tab_box[2 * (size_t)h + 1] = make_float4(bhi[0], bhi[1], bhi[2], 0.f);
-        } else {
-            atomicOr(bigbits + (pj >> 5), 1u << (pj & 31));
-        }
-    }
     if (w == 0) {
-        float v[6];
+        // exclusive prefix of the 32 warp counts, one global reservation for the whole block
+        unsigned v = s_wcnt[lane], x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned y = __shfl_up_sync(GSX_FULL, x, o);
+            if (lane >= o) x += y;
+        }
+        s_wcnt[lane] = x - v;
+        if (lane == 31) {
+            unsigned base = 0;
+            if (x) {
+                base = atomicAdd(sl.count, x);
+                if (base + x > sl.capacity) {
+                    atomicExch(sl.count + 1, 1u);
+                    base = 0xffffffffu;
+                }
+            }
+            s_base = base;
+        }
+        float vb[6];
 #pragma unroll
         for (int a = 0; a < 6; ++a) {
-            v[a] = sm[a][lane];
+            vb[a] = sm[a][lane];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                float t = __shfl_xor_sync(GSX_FULL, v[a], o);
-                v[a] = a < 3 ? fminf(v[a], t) : fmaxf(v[a], t);
+                float t = __shfl_xor_sync(GSX_FULL, vb[a], o);
+                vb[a] = a < 3 ? fminf(vb[a], t) : fmaxf(vb[a], t);
             }
         }
         if (lane == 0) {
-            saabb[2 * (int64_t)blockIdx.x] = make_float4(v[0], v[1], v[2], v[3]);
-            saabb[2 * (int64_t)blockIdx.x + 1] = make_float4(v[4], v[5], 0.f, 0.f);
+            saabb[2 * (int64_t)blockIdx.x] = make_float4(vb[0], vb[1], vb[2], vb[3]);
+            saabb[2 * (int64_t)blockIdx.x + 1] = make_float4(vb[4], vb[5], 0.f, 0.f);
+        }
+    }
+    __syncthreads();
+    if (start && s_base != 0xffffffffu)
+        sl.pos[s_base + s_wcnt[w] + __popc(sb & ((1u << lane) - 1u))] = (unsigned)j;
+}
+
+__global__ void __launch_bounds__(256)
+    k_sor_bucket_tail(const float4* __restrict__ spos, const uint8_t* __restrict__ flags, int64_t n, float bx, float by,
+                      float bz, float cell, uint64_t M64, int2* __restrict__ tab_se, float4* __restrict__ tab_box,
+                      uint32_t* __restrict__ bigbits, StartList sl) {
+    if (sl.count[1]) return;   // list overflow: the re-hashing path handles everything
+    const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= sl.count[0]) return;
+    const int64_t pj = sl.pos[t];
+    const float4 p = spos[pj];
+    const uint32_t h = bucket_of(p.x, p.y, p.z, bx, by, bz, cell, n, M64);
+    float blo[3] = {p.x, p.y, p.z}, bhi[3] = {p.x, p.y, p.z};
+    int64_t u = pj + 1;
+    const int64_t lim = pj + kSmallBucket < n ? pj + kSmallBucket : n;
+    for (; u < lim; ++u) {
+        if (flags[u] & 1) break;
+        const float4 c = spos[u];
+        blo[0] = fminf(blo[0], c.x), blo[1] = fminf(blo[1], c.y), blo[2] = fminf(blo[2], c.z);
+        bhi[0] = fmaxf(bhi[0], c.x), bhi[1] = fmaxf(bhi[1], c.y), bhi[2] = fmaxf(bhi[2], c.z);
+    }
+    const bool closed = u == n || (flags[u] & 1);
+    if (closed) {
+        tab_se[h] = make_int2((int)pj, (int)u);
+        tab_box[2 * (size_t)h] = make_float4(blo[0], blo[1], blo[2], 0.f);
+        tab_box[2 * (size_t)h + 1] = make_float4(bhi[0], bhi[1], bhi[2], 0.f);
+    } else {
+        tab_se[h].x = (int)pj;   // the end comes from k_sor_big_buckets
+        atomicOr(bigbits + (pj >> 5), 1u << (pj & 31));
+    }
+}
+
+// the few buckets longer than kSmallBucket: one warp per chunk that holds such a start
+__global__ void __launch_bounds__(256)
+    k_sor_big_buckets(const uint32_t* __restrict__ bigbits, const uint32_t* __restrict__ startbits,
+                      const float4* __restrict__ spos, const float4* __restrict__ caabb, int64_t n, float bx, float by,
+                      float bz, float cell, uint64_t M64, int2* __restrict__ tab_se, float4* __restrict__ tab_box,
+                      StartList sl) {
+    if (sl.count[1]) return;
+    const int lane = lane_id();
+    const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (chunk * 32 >= n) return;
+    unsigned m = bigbits[chunk];
+    const int64_t nchunk = (n + 31) >> 5;
+    while (m) {
+        const int src = __ffs(m) - 1;
+        m &= m - 1;
+        const int64_t s = chunk * 32 + src;
+        // end = next bucket start after s: first in this chunk's word, then 32 words at a time
+        int64_t end = n;
+        {
+            const unsigned rest = src == 31 ? 0u : (startbits[chunk] & (0xffffffffu << (src + 1)));
+            if (rest) {
+                end = chunk * 32 + __ffs(rest) - 1;
+            } else {
+                for (int64_t c0 = chunk + 1; c0 < nchunk; c0 += 32) {
+                    const int64_t c = c0 + lane;
+                    const unsigned wv = c < nchunk ? startbits[c] : 0u;
+                    const unsigned any = __ballot_sync(GSX_FULL, wv != 0u);
+                    if (any) {
+                        const int l = __ffs(any) - 1;
+                        const unsigned word = __shfl_sync(GSX_FULL, wv, l);
+                        end = (c0 + l) * 32 + __ffs(word) - 1;
+                        break;
+                    }
+                }
+            }
+        }
+        const float4 p0 = spos[s];
+        const uint32_t hb = bucket_of(p0.x, p0.y, p0.z, bx, by, bz, cell, n, M64);
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        int64_t cf = (s + 31) >> 5, cl = end >> 5;  // full chunks [cf, cl)
+        int64_t head_end = cf * 32, tail_begin = cl * 32;
+        if (cf > cl) {
+            head_end = end;
+            tail_begin = end;
+            cf = cl = 0;
+        }
+        for (int64_t t = s + lane; t < head_end; t += 32) {
+            float4 p = spos[t];
+            lo[0] = fminf(lo[0], p.x), lo[1] = fminf(lo[1], p.y), lo[2] = fminf(lo[2], p.z);
+            hi[0] = fmaxf(hi[0], p.x), hi[1] = fmaxf(hi[1], p.y), hi[2] = fmaxf(hi[2], p.z);
+        }
+        for (int64_t c = cf + lane; c < cl; c += 32) {
+            float4 a = caabb[2 * c], b = caabb[2 * c + 1];
+            lo[0] = fminf(lo[0], a.x), lo[1] = fminf(lo[1], a.y), lo[2] = fminf(lo[2], a.z);
+            hi[0] = fmaxf(hi[0], a.w), hi[1] = fmaxf(hi[1], b.x), hi[2] = fmaxf(hi[2], b.y);
+        }
+        for (int64_t t = tail_begin + lane; t < end; t += 32) {
+            float4 p = spos[t];
+            lo[0] = fminf(lo[0], p.x), lo[1] = fminf(lo[1], p.y), lo[2] = fminf(lo[2], p.z);
+            hi[0] = fmaxf(hi[0], p.x), hi[1] = fmaxf(hi[1], p.y), hi[2] = fmaxf(hi[2], p.z);
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = ord_to_float(__reduce_min_sync(GSX_FULL, float_to_ord(lo[a])));
+            hi[a] = ord_to_float(__reduce_max_sync(GSX_FULL, float_to_ord(hi[a])));
+        }
+        if (lane == 0) {
+            tab_se[hb].y = (int)end;
+            tab_box[2 * (size_t)hb] = make_float4(lo[0], lo[1], lo[2], 0.f);
+            tab_box[2 * (size_t)hb + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
         }
     }
 }
 
-// table, boxes and bucket boxes from the sorted order (shared tail of the single-GPU and the distributed build)
 template <bool GATHER>
 static int sor_finish(const float* xyz, int64_t n, const float* bmin, float cell, SorWs& w, cudaStream_t st) {
     const uint64_t M64 = 0xFFFFFFFFFFFFFFFFull / (uint64_t)n;
     GSX_CUDA_CHECK(cudaMemsetAsync(w.tab_se, 0, (size_t)n * sizeof(int2), st));
     k_sor_finish<GATHER><<<(int)((n + 1023) / 1024), 1024, 0, st>>>(xyz, w.order, w.keys_sorted, w.spos, n, bmin[0],
                                                                     bmin[1], bmin[2], cell, M64, w.tab_se, w.startbits,
-                                                                    w.cellbits, w.caabb, w.saabb);
+                                                                    w.cellbits, w.caabb, w.saabb, nullptr);
     GSX_KERNEL_CHECK();
     k_sor_bucket_boxes<<<(int)((n + 255) / 256), 256, 0, st>>>(w.startbits, w.spos, w.caabb, w.tab_se, n, bmin[0],
-                                                               bmin[1], bmin[2], cell, M64, w.tab_box);
+                                                               bmin[1], bmin[2], cell, M64, w.tab_box, nullptr);
     GSX_KERNEL_CHECK();
     return GSX_OK;
 }
@@ -695,15 +803,31 @@ int sor_build_from_sorted(const float4* spos_in, const uint8_t* flags, int64_t n
     w.order = nullptr;
     if (!flags) return sor_finish<false>(nullptr, n, bmin, cell, w, st);
     const uint64_t M64 = 0xFFFFFFFFFFFFFFFFull / (uint64_t)n;
+    const int64_t nchunk = (n + 31) / 32;
+    StartList sl;
+    sl.count = w.counters + 8;                       // [8] count, [9] overflow
+    sl.pos = reinterpret_cast<unsigned int*>(w.startlist);
+    sl.capacity = (unsigned)(n / 8 + 1024);
     GSX_CUDA_CHECK(cudaMemsetAsync(w.tab_se, 0, (size_t)n * sizeof(int2), st));
-    GSX_CUDA_CHECK(cudaMemsetAsync(w.bigbits, 0, (size_t)((n + 31) / 32) * sizeof(uint32_t), st));
-    k_sor_finish_flags<<<(int)((n + 1023) / 1024), 1024, 0, st>>>(w.spos, flags, n, bmin[0], bmin[1], bmin[2], cell, M64,
-                                                                  w.tab_se, w.tab_box, w.startbits, w.cellbits, w.bigbits,
-                                                                  w.caabb, w.saabb);
+    GSX_CUDA_CHECK(cudaMemsetAsync(w.bigbits, 0, (size_t)nchunk * sizeof(uint32_t), st));
+    GSX_CUDA_CHECK(cudaMemsetAsync(sl.count, 0, 2 * sizeof(unsigned int), st));
+    k_sor_finish_flags<<<(int)((n + 1023) / 1024), 1024, 0, st>>>(w.spos, flags, n, w.startbits, w.cellbits, w.caabb,
+                                                                  w.saabb, sl);
     GSX_KERNEL_CHECK();
-    // only the buckets longer than kSmallBucket are left (their chunks' boxes are complete now)
-    k_sor_bucket_boxes<<<(int)((n + 255) / 256), 256, 0, st>>>(w.bigbits, w.spos, w.caabb, w.tab_se, n, bmin[0],
-                                                               bmin[1], bmin[2], cell, M64, w.tab_box);
+    const unsigned tail_blocks = (sl.capacity + 255) / 256;   // upper bound of the list length (threads beyond it exit)
+    k_sor_bucket_tail<<<tail_blocks, 256, 0, st>>>(w.spos, flags, n, bmin[0], bmin[1], bmin[2], cell, M64, w.tab_se,
+                                                   w.tab_box, w.bigbits, sl);
+    GSX_KERNEL_CHECK();
+    k_sor_big_buckets<<<(int)((n + 255) / 256), 256, 0, st>>>(w.bigbits, w.startbits, w.spos, w.caabb, n, bmin[0],
+                                                              bmin[1], bmin[2], cell, M64, w.tab_se, w.tab_box, sl);
+    GSX_KERNEL_CHECK();
+    // overflow fallback (average bucket < 8 points): the re-hashing pair, gated on the device-side flag
+    k_sor_finish<false><<<(int)((n + 1023) / 1024), 1024, 0, st>>>(nullptr, nullptr, nullptr, w.spos, n, bmin[0], bmin[1],
+                                                                   bmin[2], cell, M64, w.tab_se, w.startbits, w.cellbits,
+                                                                   w.caabb, w.saabb, sl.count + 1);
+    GSX_KERNEL_CHECK();
+    k_sor_bucket_boxes<<<(int)((n + 255) / 256), 256, 0, st>>>(w.startbits, w.spos, w.caabb, w.tab_se, n, bmin[0],
+                                                              bmin[1], bmin[2], cell, M64, w.tab_box, sl.count + 1);
     GSX_KERNEL_CHECK();
     return GSX_OK;
 }

@@ -21,6 +21,7 @@ struct SorWs {
     float4* saabb;  // same per 1024-point super
     float* partial;
     float* minmax;
+    uint32_t* startlist;  // positions of the bucket starts, n/8 + 1024 entries (distributed stage C)
     unsigned int* counters;
     unsigned long long* stats;
     float* meanstd;

@@ -128,9 +128,25 @@ __device__ __forceinline__ void combine_node(int64_t n, int dmax, int d, uint32_
     slot[li] = __fadd_rn(slot[li], slot[ri]);
 }
 
-__global__ void __launch_bounds__(256) k_pw_level(int64_t n, int dmax, int d, float* slot) {
-    uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u < (1u << d)) combine_node(n, dmax, d, u, slot);
+// levels dhi..dlo in ONE launch: block b owns the subtree under node b of depth dlo (its slots are touched by no other
+// block), so up to 9 tree levels cost one launch instead of nine (the level kernels were ~20 launches of a few
+// microseconds each per mean_std, most of its time at 10 M elements)
+__global__ void __launch_bounds__(256) k_pw_mid(int64_t n, int dmax, int dhi, int dlo, float* slot) {
+    for (int d = dhi; d >= dlo; --d) {
+        if (threadIdx.x < (1u << (d - dlo))) combine_node(n, dmax, d, (blockIdx.x << (d - dlo)) + threadIdx.x, slot);
+        __syncthreads();
+    }
+}
+
+// levels dmax-1 .. 10, nine at a time; returns the next level to combine (<= 9)
+static int pairwise_mid_levels(int64_t n, int dmax, float* slot, cudaStream_t st) {
+    int d = dmax - 1;
+    while (d > 9) {
+        const int dlo = d - 8 > 10 ? d - 8 : 10;
+        k_pw_mid<<<1u << dlo, 1u << (d - dlo), 0, st>>>(n, dmax, d, dlo, slot);
+        d = dlo - 1;
+    }
+    return d;
 }
 
 // levels dtop..0 in one block, then the final division (and sqrt for the variance pass)
@@ -152,11 +168,8 @@ static int pairwise_pass(const float* a, int64_t n, int dmax, float* slot, float
     uint32_t leaves = 1u << dmax;
     k_pw_leaves<SQ><<<(unsigned)(((uint64_t)leaves * 8 + 127) / 128), 128, 0, st>>>(a, n, dmax, out, slot);
     GSX_KERNEL_CHECK();
-    int d = dmax - 1;
-    for (; d > 9; --d) {
-        k_pw_level<<<((1u << d) + 255) / 256, 256, 0, st>>>(n, dmax, d, slot);
-        GSX_KERNEL_CHECK();
-    }
+    const int d = pairwise_mid_levels(n, dmax, slot, st);
+    GSX_KERNEL_CHECK();
     k_pw_top<SQ><<<1, 1024, 0, st>>>(n, dmax, d, slot, out);  // d may be -1 (single leaf): loop is skipped
     GSX_KERNEL_CHECK();
     return GSX_OK;
@@ -238,11 +251,8 @@ int pairwise_leaves_dist(const float* a_local, int64_t base, int64_t n_local, in
 
 int pairwise_finish(float* slot, int64_t n, int sq, float* meanstd, cudaStream_t st) {
     int dmax = pairwise_depth(n);
-    int d = dmax - 1;
-    for (; d > 9; --d) {
-        k_pw_level<<<((1u << d) + 255) / 256, 256, 0, st>>>(n, dmax, d, slot);
-        GSX_KERNEL_CHECK();
-    }
+    const int d = pairwise_mid_levels(n, dmax, slot, st);
+    GSX_KERNEL_CHECK();
     if (sq) k_pw_top<true><<<1, 1024, 0, st>>>(n, dmax, d, slot, meanstd);
     else k_pw_top<false><<<1, 1024, 0, st>>>(n, dmax, d, slot, meanstd);
     GSX_KERNEL_CHECK();

@@ -51,8 +51,9 @@ def workspace(n: int, device) -> torch.Tensor:
     return torch.empty(nbytes, dtype=torch.uint8, device=device)
 
 
-def build_grid(xyz: torch.Tensor, ws: torch.Tensor | None = None) -> SorGrid:
-    """gpu_ops.py:203-237 on device (one 24-byte D2H for the cell size)."""
+def build_grid(xyz: torch.Tensor, ws: torch.Tensor | None = None, cell_scale: float = 1.0) -> SorGrid:
+    """gpu_ops.py:203-237 on device (one 24-byte D2H for the cell size).  `cell_scale` != 1 is a test hook (a finer
+    grid than the reference's, to reach the many-tiny-buckets paths of the build)."""
     _check_xyz(xyz)
     n = xyz.shape[0]
     if ws is None:
@@ -63,6 +64,8 @@ def build_grid(xyz: torch.Tensor, ws: torch.Tensor | None = None) -> SorGrid:
     cell = float(lib.gsx_sor_cell_size(mm.ctypes.data_as(C.POINTER(C.c_float)), n))
     if cell != cell:
         raise _abi.GsxError("sor: non-finite coordinates")
+    if cell_scale != 1.0:
+        cell = float(np.float32(cell * cell_scale))
     bmin = mm[:3].copy()
     check(lib.gsx_sor_build(_ptr(xyz), n, bmin.ctypes.data_as(C.POINTER(C.c_float)), cell, _ptr(ws), ws.numel(),
                             _stream()), "gsx_sor_build")

@@ -45,7 +45,7 @@ import numpy as np  # noqa: E402
 K_SOR = 16
 SIGMA = 2.0
 L2_FLUSH_BYTES = 256 << 20
-REFERENCE_BUDGET_S = 540.0   # the reference arm sizes its per-step sample so that the whole run fits this
+REFERENCE_BUDGET_S = 360.0   # the reference arm sizes its per-step sample so that the whole run fits this
 
 
 def parse():

@@ -93,10 +93,13 @@ def test_mean_std_matches_numpy(cuda, gsx_lib):
         assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), n
 
 
-def test_build_from_sorted_equals_build(cuda, gsx_lib):
+@pytest.mark.parametrize("cell_scale", [1.0, 0.25])
+def test_build_from_sorted_equals_build(cuda, gsx_lib, cell_scale):
     """The stages of the distributed build on one GPU: partition by owner (3 pretend owners) -> per-owner sort
     -> concatenation in owner order -> build_from_sorted must give the same mean distances as the one-shot
-    build (and as the oracle)."""
+    build (and as the oracle).  cell_scale 1: the reference's grid (~46 points per bucket, 79 buckets longer than 64
+    -> the per-start threads plus the long-bucket kernel); 0.25: ~3 points per bucket, which overflows the start list
+    (n/8 + 1024 entries) and must fall through to the re-hashing kernels on the device."""
     import ctypes as C
     import torch
     import oracle
@@ -106,7 +109,7 @@ def test_build_from_sorted_equals_build(cuda, gsx_lib):
     xyz_np = synth.xyz(200_000, "mixed")
     xyz = torch.from_numpy(xyz_np).to(cuda)
     n = xyz.shape[0]
-    ref = sor.build_grid(xyz)
+    ref = sor.build_grid(xyz, cell_scale=cell_scale)
     bminp = ref.bmin.ctypes.data_as(C.POINTER(C.c_float))
     world = 3
     ws = sor.workspace(n, cuda)
@@ -118,7 +121,7 @@ def test_build_from_sorted_equals_build(cuda, gsx_lib):
     assert c[0] == 0 and c[-1] == n and all(c[i] <= c[i + 1] for i in range(world))
     assert sorted(pos4[:, 3].view(torch.int32).tolist()) == list(range(n))      # a permutation of the slab
     off = lib.gsx_sor_spos_offset(n)
-    want = {mode: oracle.sor_taichi_mean_dists(xyz_np, 16, mode) for mode in ("i32wrap", "i64")}
+    want = {mode: oracle.sor_taichi_mean_dists(xyz_np, 16, mode) for mode in ("i32wrap", "i64")} if cell_scale == 1.0 else {}
     for with_flags in (False, True):   # stage C re-hashing every point / consuming the owners' per-point flags
         ws2 = torch.empty(lib.gsx_sor_grid_workspace_bytes(n), dtype=torch.uint8, device=cuda)   # grid-only blob
         spos_full = ws2[off: off + n * 16].view(torch.float32).view(n, 4)
@@ -137,7 +140,8 @@ def test_build_from_sorted_equals_build(cuda, gsx_lib):
             a = sor.mean_dists(ref, 16, mode).cpu().numpy()
             b = sor.mean_dists(grid2, 16, mode).cpu().numpy()
             assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (with_flags, mode)
-            assert np.array_equal(a.view(np.uint32), want[mode].view(np.uint32))
+            if want:
+                assert np.array_equal(a.view(np.uint32), want[mode].view(np.uint32))
             # cost-balanced sharding: 3 pretend ranks, batches dealt round-robin, union == the whole result
             u = torch.zeros(n, dtype=torch.float32, device=cuda)
             for r in range(3):
