@@ -83,8 +83,6 @@ SorWs sor_carve(void* ws, int64_t ws_bytes, int64_t n, size_t sort_ws_bytes) {
     w.grid_total = align_up(c.off, 256);
     w.keys0 = c.take<uint64_t>(n);
     w.keys1 = c.take<uint64_t>(n);
-    w.vals0 = c.take<int32_t>(n);
-    w.vals1 = c.take<int32_t>(n);
     w.sort_ws_bytes = sort_ws_bytes;
     w.sort_ws = c.take<char>(sort_ws_bytes);
     w.total = align_up(c.off, 256);
@@ -222,13 +220,48 @@ __device__ __forceinline__ uint64_t bucket_key(float x, float y, float z, float 
     return ((uint64_t)h << kMortonBits) | (uint64_t)mort;
 }
 
+// The sort works on ONE 64-bit word per point: [ bucket | Morton (top mort_bits of the kMortonBits code) | index ].
+// Only the bits above the index are sorted (stable LSD passes => equal keys stay in index order, as with a separate
+// payload), and a pass moves 8 bytes per point instead of 12.  The Morton field takes what is left of the 64 bits
+// after the bucket and the index (15 bits up to 16.7 M points, 9 at 80 M, 3 at 1 B): it only orders points INSIDE a
+// bucket, which never changes a result.
+struct PackFmt {
+    int idx_bits, mort_bits, bucket_bits;
+    __host__ __device__ int key_shift() const { return idx_bits + mort_bits; }     // word >> key_shift = bucket
+    __host__ __device__ uint64_t idx_mask() const { return (1ull << idx_bits) - 1ull; }
+    __host__ __device__ int sort_begin() const { return idx_bits; }
+    __host__ __device__ int sort_end() const { return idx_bits + mort_bits + bucket_bits; }
+};
+
+static int bits_for(int64_t n) {   // smallest b with 2^b >= n (at least 1)
+    int b = 1;
+    while (((int64_t)1 << b) < n) ++b;
+    return b;
+}
+
+static PackFmt pack_fmt(int64_t n_items, int64_t n_buckets) {
+    PackFmt f;
+    f.idx_bits = bits_for(n_items);
+    f.bucket_bits = bits_for(n_buckets);
+    int avail = 64 - f.idx_bits - f.bucket_bits;
+    if (avail > kMortonBits) avail = kMortonBits;
+    f.mort_bits = avail < 0 ? 0 : avail - avail % 3;
+    return f;
+}
+
+__device__ __forceinline__ uint64_t pack_word(uint64_t key /* bucket << kMortonBits | morton */, uint64_t bucket_sub,
+                                              int64_t idx, PackFmt f) {
+    const uint64_t bucket = (key >> kMortonBits) - bucket_sub;
+    const uint64_t mort = (key & ((1ull << kMortonBits) - 1ull)) >> (kMortonBits - f.mort_bits);
+    return (((bucket << f.mort_bits) | mort) << f.idx_bits) | (uint64_t)idx;
+}
+
 __global__ void __launch_bounds__(256) k_sor_keys(const float* __restrict__ xyz, int64_t n, float bx, float by,
-                                                  float bz, float cell, uint64_t M64,
-                                                  uint64_t* __restrict__ keys, int32_t* __restrict__ vals) {
+                                                  float bz, float cell, uint64_t M64, PackFmt f,
+                                                  uint64_t* __restrict__ keys) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    keys[i] = bucket_key(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], bx, by, bz, cell, n, M64);
-    vals[i] = (int32_t)i;
+    keys[i] = pack_word(bucket_key(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], bx, by, bz, cell, n, M64), 0, i, f);
 }
 
 // gpu_ops.py:228-237 in one pass over the hash-sorted order.  One block = 1024 sorted points = one "super", one
@@ -248,7 +281,7 @@ __device__ __forceinline__ float ord_to_float(uint32_t o) {
 
 template <bool GATHER>
 __global__ void __launch_bounds__(1024)
-    k_sor_finish(const float* __restrict__ xyz, const int32_t* __restrict__ order, const uint64_t* __restrict__ keys,
+    k_sor_finish(const float* __restrict__ xyz, const uint64_t* __restrict__ keys, PackFmt fmt,
                  float4* __restrict__ spos, int64_t n, float bx, float by, float bz, float cell, uint64_t M64,
                  int2* __restrict__ tab_se, uint32_t* __restrict__ startbits, uint32_t* __restrict__ cellbits,
                  float4* __restrict__ caabb, float4* __restrict__ saabb, const unsigned int* __restrict__ gate) {
@@ -258,7 +291,7 @@ __global__ void __launch_bounds__(1024)
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     uint32_t h = 0xffffffffu;
     auto hash_at = [&](int64_t t) -> uint32_t {
-        if (GATHER) return (uint32_t)(keys[t] >> kMortonBits);
+        if (GATHER) return (uint32_t)(keys[t] >> fmt.key_shift());
         const float4 q = spos[t];
         return bucket_of(q.x, q.y, q.z, bx, by, bz, cell, n, M64);
     };
@@ -266,10 +299,11 @@ __global__ void __launch_bounds__(1024)
     if (j < n) {
         float x, y, z;
         if (GATHER) {
-            const int32_t idx = order[j];
+            const uint64_t word = keys[j];
+            const int32_t idx = (int32_t)(word & fmt.idx_mask());
             x = xyz[3 * (int64_t)idx], y = xyz[3 * (int64_t)idx + 1], z = xyz[3 * (int64_t)idx + 2];
             spos[j] = make_float4(x, y, z, __int_as_float(idx));
-            h = (uint32_t)(keys[j] >> kMortonBits);
+            h = (uint32_t)(word >> fmt.key_shift());
         } else {
             const float4 p = spos[j];
             x = p.x, y = p.y, z = p.z;
@@ -619,10 +653,10 @@ __global__ void __launch_bounds__(256)
 }
 
 template <bool GATHER>
-static int sor_finish(const float* xyz, int64_t n, const float* bmin, float cell, SorWs& w, cudaStream_t st) {
+static int sor_finish(const float* xyz, int64_t n, const float* bmin, float cell, SorWs& w, PackFmt fmt, cudaStream_t st) {
     const uint64_t M64 = 0xFFFFFFFFFFFFFFFFull / (uint64_t)n;
     GSX_CUDA_CHECK(cudaMemsetAsync(w.tab_se, 0, (size_t)n * sizeof(int2), st));
-    k_sor_finish<GATHER><<<(int)((n + 1023) / 1024), 1024, 0, st>>>(xyz, w.order, w.keys_sorted, w.spos, n, bmin[0],
+    k_sor_finish<GATHER><<<(int)((n + 1023) / 1024), 1024, 0, st>>>(xyz, w.keys_sorted, fmt, w.spos, n, bmin[0],
                                                                     bmin[1], bmin[2], cell, M64, w.tab_se, w.startbits,
                                                                     w.cellbits, w.caabb, w.saabb, nullptr);
     GSX_KERNEL_CHECK();
@@ -635,17 +669,16 @@ static int sor_finish(const float* xyz, int64_t n, const float* bmin, float cell
 int sor_build(const float* xyz, int64_t n, const float* bmin, float cell, SorWs& w, cudaStream_t st) {
     GSX_NVTX("gsx::sor_build");
     int blocks = (int)((n + 255) / 256);
+    const PackFmt fmt = pack_fmt(n, n);
     k_sor_keys<<<blocks, 256, 0, st>>>(xyz, n, bmin[0], bmin[1], bmin[2], cell, 0xFFFFFFFFFFFFFFFFull / (uint64_t)n,
-                                       w.keys0, w.vals0);
+                                       fmt, w.keys0);
     GSX_KERNEL_CHECK();
-    int hash_bits = 1;
-    while (((int64_t)1 << hash_bits) < n) ++hash_bits;
     {
-        int rc = radix_sort_pairs(w.keys0, w.keys1, w.vals0, w.vals1, n, 0, kMortonBits + hash_bits, w.sort_ws,
-                                  w.sort_ws_bytes, &w.keys_sorted, &w.order, st);
+        int rc = radix_sort_keys(w.keys0, w.keys1, n, fmt.sort_begin(), fmt.sort_end(), w.sort_ws, w.sort_ws_bytes,
+                                 &w.keys_sorted, st);
         if (rc) return rc;
     }
-    return sor_finish<true>(xyz, n, bmin, cell, w, st);
+    return sor_finish<true>(xyz, n, bmin, cell, w, fmt, st);
 }
 
 // ------------------------------------------------------------------ distributed build (one process per GPU)
@@ -657,28 +690,26 @@ int sor_build(const float* xyz, int64_t n, const float* bmin, float cell, SorWs&
 // stage A: owner rank of every slab point (owner o holds the buckets [ceil(o*N/G), ceil((o+1)*N/G)))
 __global__ void __launch_bounds__(256) k_sor_owner_keys(const float* __restrict__ xyz, int64_t n, int64_t n_global,
                                                         int world, float bx, float by, float bz, float cell,
-                                                        uint64_t M64, uint64_t* __restrict__ keys,
-                                                        int32_t* __restrict__ vals) {
+                                                        uint64_t M64, int idx_bits, uint64_t* __restrict__ keys) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint64_t h = bucket_key(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], bx, by, bz, cell, n_global, M64) >> kMortonBits;
     // o = floor(h*G/N) satisfies ceil(o*N/G) <= h; it is the owner unless h < ceil(o*N/G) can happen -- it cannot:
     // o*N/G <= h  =>  ceil(o*N/G) <= h because h is an integer.
-    keys[i] = (h * (uint64_t)world) / (uint64_t)n_global;
-    vals[i] = (int32_t)i;
+    keys[i] = (((h * (uint64_t)world) / (uint64_t)n_global) << idx_bits) | (uint64_t)i;   // owner | slab index
 }
 
 __global__ void __launch_bounds__(256) k_sor_gather_slab(const float* __restrict__ xyz,
-                                                         const int32_t* __restrict__ order, int64_t n,
+                                                         const uint64_t* __restrict__ words, uint64_t idx_mask, int64_t n,
                                                          int64_t idx_base, float4* __restrict__ pos4) {
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
-    int32_t idx = order[j];
+    int32_t idx = (int32_t)(words[j] & idx_mask);
     pos4[j] = make_float4(xyz[3 * (int64_t)idx], xyz[3 * (int64_t)idx + 1], xyz[3 * (int64_t)idx + 2],
                           __int_as_float((int)(idx_base + idx)));
 }
 
-__global__ void k_sor_owner_counts(const uint64_t* __restrict__ owners_sorted, int64_t n, int world,
+__global__ void k_sor_owner_counts(const uint64_t* __restrict__ owners_sorted, int idx_bits, int64_t n, int world,
                                    long long* __restrict__ cuts) {
     // cuts[o] = first sorted position whose owner is >= o (o = 0..world); one thread per boundary, binary search
     int o = threadIdx.x;
@@ -686,15 +717,9 @@ __global__ void k_sor_owner_counts(const uint64_t* __restrict__ owners_sorted, i
     int64_t lo = 0, hi = n;
     while (lo < hi) {
         int64_t mid = (lo + hi) >> 1;
-        if (owners_sorted[mid] < (uint64_t)o) lo = mid + 1; else hi = mid;
+        if ((owners_sorted[mid] >> idx_bits) < (uint64_t)o) lo = mid + 1; else hi = mid;
     }
     cuts[o] = lo;
-}
-
-static int hash_bits_of(int64_t n) {
-    int b = 1;
-    while (((int64_t)1 << b) < n) ++b;
-    return b;
 }
 
 int sor_dist_local_run(const float* xyz, int64_t n_local, int64_t idx_base, int64_t n_global, int world,
@@ -707,54 +732,51 @@ int sor_dist_local_run(const float* xyz, int64_t n_local, int64_t idx_base, int6
         return GSX_OK;
     }
     int blocks = (int)((n_local + 255) / 256);
+    const int idx_bits = bits_for(n_local);
     k_sor_owner_keys<<<blocks, 256, 0, st>>>(xyz, n_local, n_global, world, bmin[0], bmin[1], bmin[2], cell,
-                                             0xFFFFFFFFFFFFFFFFull / (uint64_t)n_global, w.keys0, w.vals0);
+                                             0xFFFFFFFFFFFFFFFFull / (uint64_t)n_global, idx_bits, w.keys0);
     GSX_KERNEL_CHECK();
     uint64_t* ks = nullptr;
-    int32_t* order = nullptr;
-    int rc = radix_sort_pairs(w.keys0, w.keys1, w.vals0, w.vals1, n_local, 0, 8, w.sort_ws, w.sort_ws_bytes, &ks,
-                              &order, st);  // one stable pass: a partition by owner
+    int rc = radix_sort_keys(w.keys0, w.keys1, n_local, idx_bits, idx_bits + 8, w.sort_ws, w.sort_ws_bytes, &ks,
+                             st);  // one stable pass: a partition by owner
     if (rc) return rc;
-    k_sor_gather_slab<<<blocks, 256, 0, st>>>(xyz, order, n_local, idx_base, pos4_out);
+    k_sor_gather_slab<<<blocks, 256, 0, st>>>(xyz, ks, (1ull << idx_bits) - 1ull, n_local, idx_base, pos4_out);
     GSX_KERNEL_CHECK();
-    k_sor_owner_counts<<<1, 256, 0, st>>>(ks, n_local, world, cuts_dev);
+    k_sor_owner_counts<<<1, 256, 0, st>>>(ks, idx_bits, n_local, world, cuts_dev);
     GSX_KERNEL_CHECK();
     return GSX_OK;
 }
 
 // stage B: order the received runs of this rank's bucket range
-__global__ void __launch_bounds__(256) k_gather4(const float4* __restrict__ in, const int32_t* __restrict__ order,
-                                                 int64_t n, float4* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_gather4(const float4* __restrict__ in, const uint64_t* __restrict__ words,
+                                                 uint64_t idx_mask, int64_t n, float4* __restrict__ out) {
     int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n) out[j] = in[order[j]];
+    if (j < n) out[j] = in[words[j] & idx_mask];
 }
 
 // sort key of the owner's points: the bucket RELATIVE to the first bucket of the owner's range (the high log2(G) bits
 // of the absolute bucket are constant inside a range: one radix pass less from 8 ranks on)
 __global__ void __launch_bounds__(256) k_sor_keys_pos4(const float4* __restrict__ pos4, int64_t n, int64_t n_global,
                                                        float bx, float by, float bz, float cell, uint64_t M64,
-                                                       uint64_t bucket_lo, uint64_t* __restrict__ keys,
-                                                       int32_t* __restrict__ vals) {
+                                                       uint64_t bucket_lo, PackFmt f, uint64_t* __restrict__ keys) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 p = pos4[i];
-    keys[i] = bucket_key(p.x, p.y, p.z, bx, by, bz, cell, n_global, M64) - (bucket_lo << kMortonBits);
-    vals[i] = (int32_t)i;
+    keys[i] = pack_word(bucket_key(p.x, p.y, p.z, bx, by, bz, cell, n_global, M64), bucket_lo, i, f);
 }
 
 // stage B output with per-point flags for stage C: bit 0 = this sorted point starts a bucket, bit 1 = its grid cell
 // differs from the previous sorted point's (first point of a segment: both).  The owner knows the sorted keys, so
 // the ranks that receive the segment do not have to re-hash every point (their stage C is replicated work).
 __global__ void __launch_bounds__(256)
-    k_owner_gather_flags(const float4* __restrict__ in, const int32_t* __restrict__ order,
-                         const uint64_t* __restrict__ keys_sorted, int64_t m, float bx, float by, float bz, float cell,
+    k_owner_gather_flags(const float4* __restrict__ in, const uint64_t* __restrict__ keys_sorted, PackFmt fmt, int64_t m, float bx, float by, float bz, float cell,
                          float4* __restrict__ out, uint8_t* __restrict__ flags) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     __shared__ int sh_c[3][256];
     int gx = 0x7fffffff, gy = 0, gz = 0;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
     if (j < m) {
-        p = in[order[j]];
+        p = in[keys_sorted[j] & fmt.idx_mask()];
         out[j] = p;
         gx = (int)floorf(__fdiv_rn(__fsub_rn(p.x, bx), cell));
         gy = (int)floorf(__fdiv_rn(__fsub_rn(p.y, by), cell));
@@ -763,7 +785,7 @@ __global__ void __launch_bounds__(256)
     sh_c[0][threadIdx.x] = gx, sh_c[1][threadIdx.x] = gy, sh_c[2][threadIdx.x] = gz;
     __syncthreads();
     if (j >= m) return;
-    const bool start = j == 0 || (keys_sorted[j] >> kMortonBits) != (keys_sorted[j - 1] >> kMortonBits);
+    const bool start = j == 0 || (keys_sorted[j] >> fmt.key_shift()) != (keys_sorted[j - 1] >> fmt.key_shift());
     bool newcell = threadIdx.x == 0 || sh_c[0][threadIdx.x - 1] != gx || sh_c[1][threadIdx.x - 1] != gy ||
                    sh_c[2][threadIdx.x - 1] != gz;   // block edges: conservatively "new"
     flags[j] = (uint8_t)((start ? 1 : 0) | ((newcell || start) ? 2 : 0));
@@ -775,20 +797,18 @@ int sor_dist_merge(const float4* pos4_in, int64_t m, int64_t n_global, int64_t b
     if (m == 0) return GSX_OK;
     GSX_REQUIRE(bucket_lo >= 0 && bucket_lo < bucket_hi && bucket_hi <= n_global, GSX_ERR_ARG, "sor: bad bucket range");
     int blocks = (int)((m + 255) / 256);
+    const PackFmt fmt = pack_fmt(m, bucket_hi - bucket_lo);
     k_sor_keys_pos4<<<blocks, 256, 0, st>>>(pos4_in, m, n_global, bmin[0], bmin[1], bmin[2], cell,
-                                            0xFFFFFFFFFFFFFFFFull / (uint64_t)n_global, (uint64_t)bucket_lo, w.keys0,
-                                            w.vals0);
+                                            0xFFFFFFFFFFFFFFFFull / (uint64_t)n_global, (uint64_t)bucket_lo, fmt, w.keys0);
     GSX_KERNEL_CHECK();
     uint64_t* ks = nullptr;
-    int32_t* order = nullptr;
-    int rc = radix_sort_pairs(w.keys0, w.keys1, w.vals0, w.vals1, m, 0, kMortonBits + hash_bits_of(bucket_hi - bucket_lo),
-                              w.sort_ws, w.sort_ws_bytes, &ks, &order, st);
+    int rc = radix_sort_keys(w.keys0, w.keys1, m, fmt.sort_begin(), fmt.sort_end(), w.sort_ws, w.sort_ws_bytes, &ks, st);
     if (rc) return rc;
     if (flags_out)
-        k_owner_gather_flags<<<blocks, 256, 0, st>>>(pos4_in, order, ks, m, bmin[0], bmin[1], bmin[2], cell, pos4_out,
+        k_owner_gather_flags<<<blocks, 256, 0, st>>>(pos4_in, ks, fmt, m, bmin[0], bmin[1], bmin[2], cell, pos4_out,
                                                      flags_out);
     else
-        k_gather4<<<blocks, 256, 0, st>>>(pos4_in, order, m, pos4_out);
+        k_gather4<<<blocks, 256, 0, st>>>(pos4_in, ks, fmt.idx_mask(), m, pos4_out);
     GSX_KERNEL_CHECK();
     return GSX_OK;
 }
@@ -800,8 +820,7 @@ int sor_build_from_sorted(const float4* spos_in, const uint8_t* flags, int64_t n
     if (spos_in != w.spos)
         GSX_CUDA_CHECK(cudaMemcpyAsync(w.spos, spos_in, (size_t)n * sizeof(float4), cudaMemcpyDeviceToDevice, st));
     w.keys_sorted = nullptr;
-    w.order = nullptr;
-    if (!flags) return sor_finish<false>(nullptr, n, bmin, cell, w, st);
+    if (!flags) return sor_finish<false>(nullptr, n, bmin, cell, w, PackFmt{}, st);
     const uint64_t M64 = 0xFFFFFFFFFFFFFFFFull / (uint64_t)n;
     const int64_t nchunk = (n + 31) / 32;
     StartList sl;
@@ -822,7 +841,7 @@ int sor_build_from_sorted(const float4* spos_in, const uint8_t* flags, int64_t n
                                                               bmin[1], bmin[2], cell, M64, w.tab_se, w.tab_box, sl);
     GSX_KERNEL_CHECK();
     // overflow fallback (average bucket < 8 points): the re-hashing pair, gated on the device-side flag
-    k_sor_finish<false><<<(int)((n + 1023) / 1024), 1024, 0, st>>>(nullptr, nullptr, nullptr, w.spos, n, bmin[0], bmin[1],
+    k_sor_finish<false><<<(int)((n + 1023) / 1024), 1024, 0, st>>>(nullptr, nullptr, PackFmt{}, w.spos, n, bmin[0], bmin[1],
                                                                    bmin[2], cell, M64, w.tab_se, w.startbits, w.cellbits,
                                                                    w.caabb, w.saabb, sl.count + 1);
     GSX_KERNEL_CHECK();
@@ -1192,6 +1211,8 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
     }
 }
 
+#include "gsx_sor_knn16.cuh"
+
 __global__ void k_fill_f32(float* p, int64_t n, float v) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;
@@ -1210,6 +1231,25 @@ static int launch_knn(SorWs& w, int64_t q_begin, int64_t q_end, int q_stride, in
                                                       q_begin, q_end, q_stride, q_phase, K, hash_mode, bmin[0], bmin[1],
                                                       bmin[2], cell,
                                                       (uint32_t)w.n, M, stats);
+    return GSX_OK;
+}
+
+#ifndef GSX_KNN16
+#define GSX_KNN16 1   // K <= 16: two queries per warp (gsx_sor_knn16.cuh); 0 keeps the warp-per-query kernel (A/B)
+#endif
+template <bool STATS>
+static int launch_knn16(SorWs& w, int64_t q_begin, int64_t q_end, int q_stride, int q_phase, int K, int hash_mode,
+                        const float* bmin, float cell, float* final_means, unsigned long long* stats, uint64_t M,
+                        int64_t want, cudaStream_t st) {
+    int per_sm = 0;
+    GSX_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sor_knn16<STATS>, 256, 0));
+    int64_t grid = (int64_t)sm_count() * (per_sm > 0 ? per_sm : 4);
+    want = (want + 1) / 2;   // a block takes 16 batches at a time, not 8
+    if (grid > want) grid = want;
+    if (grid < 1) grid = 1;
+    k_sor_knn16<STATS><<<(int)grid, 256, 0, st>>>(w.spos, w.tab_se, w.tab_box, w.cellbits, w.caabb, w.saabb, final_means,
+                                                  w.counters, q_begin, q_end, q_stride, q_phase, K, hash_mode, bmin[0],
+                                                  bmin[1], bmin[2], cell, (uint32_t)w.n, M, stats);
     return GSX_OK;
 }
 
@@ -1235,7 +1275,10 @@ int sor_mean_dists(SorWs& w, int64_t q_begin, int64_t q_end, int q_stride, int q
     int64_t nq = (q_end - q_begin + q_stride - 1) / q_stride + kQueryBatch;   // this launch's share (upper bound)
     int64_t want = (nq + (int64_t)kQueryBatch * 8 - 1) / ((int64_t)kQueryBatch * 8);
     int rc;
-    if (stats) rc = K <= 32 ? launch_knn<1, true>(w, q_begin, q_end, q_stride, q_phase, K, hash_mode, bmin, cell, final_means, stats, M, want, st)
+    if (GSX_KNN16 && K <= 16)
+        rc = stats ? launch_knn16<true>(w, q_begin, q_end, q_stride, q_phase, K, hash_mode, bmin, cell, final_means, stats, M, want, st)
+                   : launch_knn16<false>(w, q_begin, q_end, q_stride, q_phase, K, hash_mode, bmin, cell, final_means, stats, M, want, st);
+    else if (stats) rc = K <= 32 ? launch_knn<1, true>(w, q_begin, q_end, q_stride, q_phase, K, hash_mode, bmin, cell, final_means, stats, M, want, st)
                             : launch_knn<2, true>(w, q_begin, q_end, q_stride, q_phase, K, hash_mode, bmin, cell, final_means, stats, M, want, st);
     else rc = K <= 32 ? launch_knn<1, false>(w, q_begin, q_end, q_stride, q_phase, K, hash_mode, bmin, cell, final_means, stats, M, want, st)
                       : launch_knn<2, false>(w, q_begin, q_end, q_stride, q_phase, K, hash_mode, bmin, cell, final_means, stats, M, want, st);

@@ -10,7 +10,6 @@ namespace gsx {
 struct SorWs {
     int64_t n;
     uint64_t *keys0, *keys1, *keys_sorted;
-    int32_t *vals0, *vals1, *order;
     float4* spos;   // hash-sorted positions, w = original index
     int2* tab_se;         // per bucket {start, end} in sorted order; {0,0} = empty (cell_start == -1)
     float4* tab_box;      // per bucket {lo.xyz,-},{hi.xyz,-}: exact box of its points (occupied buckets only)

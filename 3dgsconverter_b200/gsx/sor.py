@@ -185,8 +185,9 @@ def ckdtree_filter_host(data_np: np.ndarray, k: int = 25, threshold_factor: floa
     return (mask, means) if return_means else mask
 
 
-def sort_pairs(keys: torch.Tensor, vals: torch.Tensor, begin_bit: int = 0, end_bit: int = 64):
-    """In-place stable radix sort of (int64-viewed-as-uint64 keys, int32 vals) on key bits [begin,end)."""
+def sort_pairs(keys: torch.Tensor, vals: torch.Tensor | None, begin_bit: int = 0, end_bit: int = 64):
+    """In-place stable radix sort of (int64-viewed-as-uint64 keys, int32 vals) on key bits [begin,end).
+    vals=None sorts bare 64-bit words (payload packed below begin_bit), the form the grid build uses."""
     n = keys.numel()
     ws = torch.empty(lib.gsx_sort_pairs_workspace_bytes(n), dtype=torch.uint8, device=keys.device)
     check(lib.gsx_sort_pairs(_ptr(keys), _ptr(vals), n, begin_bit, end_bit, _ptr(ws), ws.numel(), _stream()),

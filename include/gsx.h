@@ -110,8 +110,10 @@ int gsx_sor_mean_dists_strided(int64_t n, int32_t stride, int32_t phase, int32_t
                                unsigned long long* stats_dev, void* stream);
 
 /* gpu_ops.py:227 (np.argsort of the bucket hashes): stable LSD radix sort, in place, of (uint64 key, int32
- * value) pairs on the key bits [begin_bit, end_bit).  The hash-grid build uses it with key =
- * hash << 15 | Morton code and value = original index. */
+ * value) pairs on the key bits [begin_bit, end_bit): 8-bit digits, one "onesweep" kernel per digit (decoupled
+ * look-back over per-tile digit counts) after a single histogram pass.  vals_dev == NULL sorts bare 64-bit words
+ * (n < 2^30): the form the hash-grid build uses, with word = bucket | in-cell Morton code | original index and only the
+ * bits above the index sorted -- 8 instead of 12 bytes moved per point and pass. */
 int64_t gsx_sort_pairs_workspace_bytes(int64_t n);
 int gsx_sort_pairs(uint64_t* keys_dev, int32_t* vals_dev, int64_t n, int32_t begin_bit, int32_t end_bit, void* ws,
                    int64_t ws_bytes, void* stream);

@@ -167,3 +167,20 @@ def test_compact_points_matches_numpy(cuda, gsx_lib):
             assert m == int(mask.sum())
             assert np.array_equal(x.cpu().numpy(), xyz[mask]) and np.array_equal(o.cpu().numpy(), op[mask])
             assert np.array_equal(idx.cpu().numpy(), np.flatnonzero(mask))
+
+
+def test_compact_points_unaligned_mask_and_chained_index(cuda, gsx_lib):
+    """mask at an odd byte offset (the 8-byte mask loads must fall back), an input row index (second filter of a chain)
+    and no opacity column."""
+    import torch
+    from gsx.pipeline import compact
+    rng = np.random.default_rng(11)
+    n = 300_007
+    xyz = rng.standard_normal((n, 3)).astype(np.float32)
+    rows = rng.permutation(10 * n)[:n].astype(np.int32)
+    mask = rng.random(n) < 0.3
+    buf = torch.zeros(n + 3, dtype=torch.uint8, device=cuda)
+    buf[3:] = torch.from_numpy(mask.view(np.uint8)).to(cuda)
+    x, o, idx, m = compact(buf[3:], torch.from_numpy(xyz).to(cuda), None, torch.from_numpy(rows).to(cuda))
+    assert o is None and m == int(mask.sum())
+    assert np.array_equal(x.cpu().numpy(), xyz[mask]) and np.array_equal(idx.cpu().numpy(), rows[mask])

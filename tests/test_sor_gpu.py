@@ -19,7 +19,7 @@ def _run(xyz_np, k, sigma, mode, cuda):
 
 @pytest.mark.parametrize("kind", ["mixed", "uniform", "clustered"])
 @pytest.mark.parametrize("mode", ["i32wrap", "i64"])
-@pytest.mark.parametrize("n,k", [(100_000, 16), (100_000, 27), (30_000, 50), (300_000, 16)])
+@pytest.mark.parametrize("n,k", [(100_000, 16), (100_000, 27), (30_000, 50), (300_000, 16), (60_000, 7), (40_000, 1)])
 def test_sor_matches_oracle(kind, mode, n, k, cuda, gsx_lib):
     import oracle
     from gsx import synth
