@@ -445,7 +445,9 @@ int gsx_kmeans_lloyd_device(const float* X_dev, const int64_t* row_off_host, int
                         assign_mode, tc_stats_dev, (cudaStream_t)stream);
 }
 
-int32_t gsx_kmeans_tensor_core_supported(int32_t K, int32_t D) { return kmeans_tc_supported(K, D) ? 1 : 0; }
+int32_t gsx_kmeans_tensor_core_supported(int32_t K, int32_t D) {
+    return kmeans_tc_supported(K, D) ? (kmeans_tc16_built() ? 3 : 1) : 0;   // bit 0: TF32 kernel, bit 1: split-bf16 build
+}
 
 int gsx_kmeans_tc_debug_scores(const float* X_dev, int64_t rows, const float* C_dev, int32_t K, int32_t D,
                                int32_t variant, float* scores_dev, void* ws, int64_t ws_bytes, void* stream) {

@@ -23,6 +23,7 @@ int kmeans_lloyd(const float* X, const int64_t* row_off, int nprob, int K, int D
                  cudaStream_t st);
 // gsx_kmeans_tc.cu
 bool kmeans_tc_supported(int K, int D);
+bool kmeans_tc16_built();
 int kmeans_assign_tc(const float* X, long long x_floats, const float* C, int* labels, const KmProb* probs_dev, int nprob,
                      int K, int D, long long tiles, int variant, int mode, float* dump, unsigned long long* stats,
                      int* err_flag_dev, cudaStream_t st);

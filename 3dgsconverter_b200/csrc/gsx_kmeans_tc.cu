@@ -36,7 +36,11 @@ namespace gsx {
 constexpr int kTcThreads = 256;   // two threads per point row (TMEM lane): they split the centroid columns
 constexpr int kTcRows = 128;      // UMMA M
 constexpr int kTcMaxN = 256;      // UMMA N limit == max centroids of the tensor-core path
-constexpr unsigned kSpinLimit = 1u << 26;  // bounded mbarrier waits: a protocol bug must not hang the GPU
+#ifndef GSX_KM_TC16
+#define GSX_KM_TC16 0   // variant B (split bf16): measured slower than TF32 and it stalls on tests/test_kmeans_prefilter_gpu.py::
+                        // test_prefilter_adversarial -- kept as a build-time experiment, not part of the shipped library
+#endif
+constexpr long long kWaitCycles = 1ll << 31;   // ~1 s: a protocol bug reports an error instead of hanging the GPU
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -49,7 +53,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 // returns false on timeout
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
-    for (unsigned spin = 0; spin < kSpinLimit; ++spin) {
+    const long long t0 = clock64();
+    for (unsigned spin = 0;; ++spin) {
+        if ((spin & 1023u) == 1023u && clock64() - t0 > kWaitCycles) break;
         uint32_t ok;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -537,6 +543,8 @@ struct Tc16Shared {
     int pbk[kTcRows];
 };
 
+#if GSX_KM_TC16
+
 template <int D, int KP>   // KP: padded K in bf16 elements, multiple of 16, >= D + 3
 __global__ void __launch_bounds__(kTcThreads, 2)
     k_km_assign_tc16(const float* __restrict__ X, long long x_floats, const float* __restrict__ C,
@@ -885,6 +893,8 @@ static int launch_tc16(const float* X, long long x_floats, const float* C, int* 
     return GSX_OK;
 }
 
+#endif  // GSX_KM_TC16
+
 template <int D, int KP>
 static int launch_tc(const float* X, long long x_floats, const float* C, int* labels, const KmProb* probs, int nprob,
                      int K, long long tiles, int variant, int mode, float* dump, unsigned long long* stats, int* err,
@@ -907,18 +917,25 @@ static int launch_tc(const float* X, long long x_floats, const float* C, int* la
     return GSX_OK;
 }
 
+bool kmeans_tc16_built() { return GSX_KM_TC16 != 0; }
+
 bool kmeans_tc_supported(int K, int D) { return (D == 9 || D == 24 || D == 45) && K >= 1 && K <= kTcMaxN; }
 
 int kmeans_assign_tc(const float* X, long long x_floats, const float* C, int* labels, const KmProb* probs_dev, int nprob,
                      int K, int D, long long tiles, int variant, int mode, float* dump, unsigned long long* stats,
                      int* err_flag_dev, cudaStream_t st) {
     if (variant == 2) {  // split-bf16 scores, single-pass epilogue
+#if !GSX_KM_TC16
+        set_error("kmeans_tc: the split-bf16 variant is a build-time experiment (compile gsx_kmeans_tc.cu with -DGSX_KM_TC16=1)");
+        return GSX_ERR_UNSUPPORTED;
+#else
         switch (D) {
             case 9: return launch_tc16<9, 16>(X, x_floats, C, labels, probs_dev, nprob, K, tiles, mode, dump, stats, err_flag_dev, st);
             case 24: return launch_tc16<24, 32>(X, x_floats, C, labels, probs_dev, nprob, K, tiles, mode, dump, stats, err_flag_dev, st);
             case 45: return launch_tc16<45, 48>(X, x_floats, C, labels, probs_dev, nprob, K, tiles, mode, dump, stats, err_flag_dev, st);
             default: set_error("kmeans_tc: unsupported D=%d", D); return GSX_ERR_UNSUPPORTED;
         }
+#endif
     }
     switch (D) {
         case 9: return launch_tc<9, 16>(X, x_floats, C, labels, probs_dev, nprob, K, tiles, variant, mode, dump, stats, err_flag_dev, st);

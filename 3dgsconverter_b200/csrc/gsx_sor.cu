@@ -280,13 +280,12 @@ __device__ __forceinline__ float ord_to_float(uint32_t o) {
 }
 
 template <bool GATHER>
-__global__ void __launch_bounds__(1024)
-    k_sor_finish(const float* __restrict__ xyz, const uint64_t* __restrict__ keys, PackFmt fmt,
-                 float4* __restrict__ spos, int64_t n, float bx, float by, float bz, float cell, uint64_t M64,
-                 int2* __restrict__ tab_se, uint32_t* __restrict__ startbits, uint32_t* __restrict__ cellbits,
-                 float4* __restrict__ caabb, float4* __restrict__ saabb, const unsigned int* __restrict__ gate) {
-    if (gate && !*gate) return;   // fallback of the flag path: runs only when its start list overflowed
-    const int64_t j = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+__device__ __forceinline__ void
+    sor_finish_tile(const int64_t tile, const float* __restrict__ xyz, const uint64_t* __restrict__ keys, PackFmt fmt,
+                    float4* __restrict__ spos, int64_t n, float bx, float by, float bz, float cell, uint64_t M64,
+                    int2* __restrict__ tab_se, uint32_t* __restrict__ startbits, uint32_t* __restrict__ cellbits,
+                    float4* __restrict__ caabb, float4* __restrict__ saabb) {
+    const int64_t j = tile * 1024 + threadIdx.x;
     const int lane = lane_id();
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     uint32_t h = 0xffffffffu;
@@ -348,7 +347,7 @@ __global__ void __launch_bounds__(1024)
     }
     __shared__ float sm[6][32];
     const int w = threadIdx.x >> 5;
-    const int64_t chunk = (int64_t)blockIdx.x * 32 + w;
+    const int64_t chunk = tile * 32 + w;
     if (lane == 0) {
         if (chunk * 32 < n) {
             startbits[chunk] = sb;
@@ -374,9 +373,34 @@ __global__ void __launch_bounds__(1024)
             }
         }
         if (lane == 0) {
-            saabb[2 * (int64_t)blockIdx.x] = make_float4(v[0], v[1], v[2], v[3]);
-            saabb[2 * (int64_t)blockIdx.x + 1] = make_float4(v[4], v[5], 0.f, 0.f);
+            saabb[2 * tile] = make_float4(v[0], v[1], v[2], v[3]);
+            saabb[2 * tile + 1] = make_float4(v[4], v[5], 0.f, 0.f);
         }
+    }
+}
+
+template <bool GATHER>
+__global__ void __launch_bounds__(1024)
+    k_sor_finish(const float* __restrict__ xyz, const uint64_t* __restrict__ keys, PackFmt fmt,
+                 float4* __restrict__ spos, int64_t n, float bx, float by, float bz, float cell, uint64_t M64,
+                 int2* __restrict__ tab_se, uint32_t* __restrict__ startbits, uint32_t* __restrict__ cellbits,
+                 float4* __restrict__ caabb, float4* __restrict__ saabb) {
+    sor_finish_tile<GATHER>(blockIdx.x, xyz, keys, fmt, spos, n, bx, by, bz, cell, M64, tab_se, startbits, cellbits, caabb,
+                            saabb);
+}
+
+// the same pass as the fallback of the flag-driven stage C: a resident-size grid that returns at once unless the start
+// list overflowed (a grid of n/1024 empty blocks would itself cost ~0.1 ms at 80 M points)
+__global__ void __launch_bounds__(1024)
+    k_sor_finish_gated(float4* __restrict__ spos, int64_t n, float bx, float by, float bz, float cell, uint64_t M64,
+                       int2* __restrict__ tab_se, uint32_t* __restrict__ startbits, uint32_t* __restrict__ cellbits,
+                       float4* __restrict__ caabb, float4* __restrict__ saabb, const unsigned int* __restrict__ gate) {
+    if (!*gate) return;
+    const int64_t tiles = (n + 1023) / 1024;
+    for (int64_t t = blockIdx.x; t < tiles; t += gridDim.x) {
+        sor_finish_tile<false>(t, nullptr, nullptr, PackFmt{}, spos, n, bx, by, bz, cell, M64, tab_se, startbits, cellbits,
+                               caabb, saabb);
+        __syncthreads();
     }
 }
 
@@ -385,14 +409,11 @@ __global__ void __launch_bounds__(1024)
 // starts among its 32 sorted positions (startbits) and reduces each bucket cooperatively (stride 32 over the
 // bucket's range; chunks that lie entirely inside the bucket contribute their box instead of their points).
 // tab_box[2h] = {lo.xyz, -}, tab_box[2h+1] = {hi.xyz, -}: 32 bytes = one DRAM sector per occupied bucket.
-__global__ void __launch_bounds__(256)
-    k_sor_bucket_boxes(const uint32_t* __restrict__ startbits, const float4* __restrict__ spos,
+__device__ __forceinline__ void
+    bucket_boxes_chunk(const int64_t chunk, const uint32_t* __restrict__ startbits, const float4* __restrict__ spos,
                        const float4* __restrict__ caabb, const int2* __restrict__ tab_se, int64_t n, float bx,
-                       float by, float bz, float cell, uint64_t M64, float4* __restrict__ tab_box,
-                       const unsigned int* __restrict__ gate) {
-    if (gate && !*gate) return;
+                       float by, float bz, float cell, uint64_t M64, float4* __restrict__ tab_box) {
     const int lane = lane_id();
-    const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (chunk * 32 >= n) return;
     unsigned m = startbits[chunk];
     // the hash and the end of every bucket that starts in this chunk: one lane per start, in parallel
@@ -444,6 +465,25 @@ __global__ void __launch_bounds__(256)
             tab_box[2 * (size_t)hb + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
         }
     }
+}
+
+__global__ void __launch_bounds__(256)
+    k_sor_bucket_boxes(const uint32_t* __restrict__ startbits, const float4* __restrict__ spos,
+                       const float4* __restrict__ caabb, const int2* __restrict__ tab_se, int64_t n, float bx,
+                       float by, float bz, float cell, uint64_t M64, float4* __restrict__ tab_box) {
+    bucket_boxes_chunk(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, startbits, spos, caabb, tab_se, n, bx, by, bz,
+                       cell, M64, tab_box);
+}
+
+__global__ void __launch_bounds__(256)
+    k_sor_bucket_boxes_gated(const uint32_t* __restrict__ startbits, const float4* __restrict__ spos,
+                             const float4* __restrict__ caabb, const int2* __restrict__ tab_se, int64_t n, float bx,
+                             float by, float bz, float cell, uint64_t M64, float4* __restrict__ tab_box,
+                             const unsigned int* __restrict__ gate) {
+    if (!*gate) return;
+    const int64_t nchunk = (n + 31) >> 5, step = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; c < nchunk; c += step)
+        bucket_boxes_chunk(c, startbits, spos, caabb, tab_se, n, bx, by, bz, cell, M64, tab_box);
 }
 
 // Stage C when the owners shipped per-point flags (bit 0 bucket start, bit 1 cell change).  Three kernels, none of
@@ -586,10 +626,18 @@ __global__ void __launch_bounds__(256)
                       StartList sl) {
     if (sl.count[1]) return;
     const int lane = lane_id();
-    const int64_t chunk = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (chunk * 32 >= n) return;
-    unsigned m = bigbits[chunk];
     const int64_t nchunk = (n + 31) >> 5;
+    // a resident-size grid sweeps the (almost empty) bit mask 32 words per warp step; the warp then handles the
+    // words that have a bit, one after the other
+    const int64_t wstep = (((int64_t)gridDim.x * blockDim.x) >> 5) * 32;
+    for (int64_t c0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32; c0 < nchunk; c0 += wstep) {
+    const uint32_t myword = c0 + lane < nchunk ? bigbits[c0 + lane] : 0u;
+    unsigned wordmask = __ballot_sync(GSX_FULL, myword != 0u);
+    while (wordmask) {
+    const int wl = __ffs(wordmask) - 1;
+    wordmask &= wordmask - 1;
+    const int64_t chunk = c0 + wl;
+    unsigned m = __shfl_sync(GSX_FULL, myword, wl);
     while (m) {
         const int src = __ffs(m) - 1;
         m &= m - 1;
@@ -601,14 +649,14 @@ __global__ void __launch_bounds__(256)
             if (rest) {
                 end = chunk * 32 + __ffs(rest) - 1;
             } else {
-                for (int64_t c0 = chunk + 1; c0 < nchunk; c0 += 32) {
-                    const int64_t c = c0 + lane;
+                for (int64_t d0 = chunk + 1; d0 < nchunk; d0 += 32) {
+                    const int64_t c = d0 + lane;
                     const unsigned wv = c < nchunk ? startbits[c] : 0u;
                     const unsigned any = __ballot_sync(GSX_FULL, wv != 0u);
                     if (any) {
                         const int l = __ffs(any) - 1;
                         const unsigned word = __shfl_sync(GSX_FULL, wv, l);
-                        end = (c0 + l) * 32 + __ffs(word) - 1;
+                        end = (d0 + l) * 32 + __ffs(word) - 1;
                         break;
                     }
                 }
@@ -650,6 +698,8 @@ __global__ void __launch_bounds__(256)
             tab_box[2 * (size_t)hb + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
         }
     }
+    }
+    }
 }
 
 template <bool GATHER>
@@ -658,10 +708,10 @@ static int sor_finish(const float* xyz, int64_t n, const float* bmin, float cell
     GSX_CUDA_CHECK(cudaMemsetAsync(w.tab_se, 0, (size_t)n * sizeof(int2), st));
     k_sor_finish<GATHER><<<(int)((n + 1023) / 1024), 1024, 0, st>>>(xyz, w.keys_sorted, fmt, w.spos, n, bmin[0],
                                                                     bmin[1], bmin[2], cell, M64, w.tab_se, w.startbits,
-                                                                    w.cellbits, w.caabb, w.saabb, nullptr);
+                                                                    w.cellbits, w.caabb, w.saabb);
     GSX_KERNEL_CHECK();
     k_sor_bucket_boxes<<<(int)((n + 255) / 256), 256, 0, st>>>(w.startbits, w.spos, w.caabb, w.tab_se, n, bmin[0],
-                                                               bmin[1], bmin[2], cell, M64, w.tab_box, nullptr);
+                                                               bmin[1], bmin[2], cell, M64, w.tab_box);
     GSX_KERNEL_CHECK();
     return GSX_OK;
 }
@@ -837,16 +887,16 @@ int sor_build_from_sorted(const float4* spos_in, const uint8_t* flags, int64_t n
     k_sor_bucket_tail<<<tail_blocks, 256, 0, st>>>(w.spos, flags, n, bmin[0], bmin[1], bmin[2], cell, M64, w.tab_se,
                                                    w.tab_box, w.bigbits, sl);
     GSX_KERNEL_CHECK();
-    k_sor_big_buckets<<<(int)((n + 255) / 256), 256, 0, st>>>(w.bigbits, w.startbits, w.spos, w.caabb, n, bmin[0],
-                                                              bmin[1], bmin[2], cell, M64, w.tab_se, w.tab_box, sl);
+    k_sor_big_buckets<<<sm_count() * 8, 256, 0, st>>>(w.bigbits, w.startbits, w.spos, w.caabb, n, bmin[0], bmin[1], bmin[2],
+                                                      cell, M64, w.tab_se, w.tab_box, sl);
     GSX_KERNEL_CHECK();
     // overflow fallback (average bucket < 8 points): the re-hashing pair, gated on the device-side flag
-    k_sor_finish<false><<<(int)((n + 1023) / 1024), 1024, 0, st>>>(nullptr, nullptr, PackFmt{}, w.spos, n, bmin[0], bmin[1],
-                                                                   bmin[2], cell, M64, w.tab_se, w.startbits, w.cellbits,
-                                                                   w.caabb, w.saabb, sl.count + 1);
+    const int resident = sm_count() * 2;
+    k_sor_finish_gated<<<resident, 1024, 0, st>>>(w.spos, n, bmin[0], bmin[1], bmin[2], cell, M64, w.tab_se, w.startbits,
+                                                  w.cellbits, w.caabb, w.saabb, sl.count + 1);
     GSX_KERNEL_CHECK();
-    k_sor_bucket_boxes<<<(int)((n + 255) / 256), 256, 0, st>>>(w.startbits, w.spos, w.caabb, w.tab_se, n, bmin[0],
-                                                              bmin[1], bmin[2], cell, M64, w.tab_box, sl.count + 1);
+    k_sor_bucket_boxes_gated<<<resident * 4, 256, 0, st>>>(w.startbits, w.spos, w.caabb, w.tab_se, n, bmin[0], bmin[1],
+                                                           bmin[2], cell, M64, w.tab_box, sl.count + 1);
     GSX_KERNEL_CHECK();
     return GSX_OK;
 }
@@ -1235,7 +1285,8 @@ static int launch_knn(SorWs& w, int64_t q_begin, int64_t q_end, int q_stride, in
 }
 
 #ifndef GSX_KNN16
-#define GSX_KNN16 1   // K <= 16: two queries per warp (gsx_sor_knn16.cuh); 0 keeps the warp-per-query kernel (A/B)
+#define GSX_KNN16 0   // 1: K <= 16 goes to the two-queries-per-warp kernel (gsx_sor_knn16.cuh) -- an A/B variant, it
+                      // measured SLOWER than the warp-per-query kernel (profiles/r02_knn16_variants.log)
 #endif
 template <bool STATS>
 static int launch_knn16(SorWs& w, int64_t q_begin, int64_t q_end, int q_stride, int q_phase, int K, int hash_mode,

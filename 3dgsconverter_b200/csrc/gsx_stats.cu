@@ -86,9 +86,17 @@ __device__ __forceinline__ float leaf_sum8(int64_t off, int64_t m, int j, Get ge
             for (int64_t i = 0; i < m; ++i) res = __fadd_rn(res, get(off + i));
         return res;
     }
-    float r = get(off + j);
+    // a leaf has at most 128 elements = 16 per lane: issue all the loads first (independent), then the ordered adds
     const int64_t body = m - (m % 8);
-    for (int64_t i = 8; i < body; i += 8) r = __fadd_rn(r, get(off + i + j));
+    const int cnt = (int)(body >> 3);
+    float vals[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k)
+        if (k < cnt) vals[k] = get(off + 8 * k + j);
+    float r = vals[0];
+#pragma unroll
+    for (int k = 1; k < 16; ++k)
+        if (k < cnt) r = __fadd_rn(r, vals[k]);
     r = __fadd_rn(r, __shfl_xor_sync(grp, r, 1));
     r = __fadd_rn(r, __shfl_xor_sync(grp, r, 2));
     r = __fadd_rn(r, __shfl_xor_sync(grp, r, 4));

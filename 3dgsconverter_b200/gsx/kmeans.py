@@ -18,7 +18,12 @@ def default_assign_mode() -> str:
 
 
 def tensor_core_supported(K: int, D: int) -> bool:
-    return bool(lib.gsx_kmeans_tensor_core_supported(int(K), int(D)))
+    return bool(lib.gsx_kmeans_tensor_core_supported(int(K), int(D)) & 1)
+
+
+def tensor_bf16_built() -> bool:
+    """The split-bf16 variant is a build-time experiment (-DGSX_KM_TC16=1), not part of the shipped library."""
+    return bool(lib.gsx_kmeans_tensor_core_supported(256, 45) & 2)
 
 
 def kmeans_lloyd_batched(X: torch.Tensor, row_off, K: int, max_iter: int, init: torch.Tensor,

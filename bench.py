@@ -426,7 +426,8 @@ def run_c2(args):
         args.hash == prof.get("hash")
     winst = prof.get("warp_instructions_per_launch") if same_cfg else None
     traffic = prof.get("dram_bytes_per_launch") if same_cfg else None
-    roofline = {"bound": "issue", "kernel": "k_sor_knn",
+    kname = (prof.get("kernel") or "k_sor_knn16 (K<=16) / k_sor_knn").split("(const")[0].replace("void ", "").strip()
+    roofline = {"bound": "issue", "kernel": kname,
                 "achieved": round(winst / (knn_avg_ms * 1e-3) / 1e9, 1) if winst else None,
                 "peak": round(issue_peak, 1), "unit": "Gwarp-instr/s",
                 "frac": round(winst / (knn_avg_ms * 1e-3) / 1e9 / issue_peak, 4) if winst else None,

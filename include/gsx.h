@@ -232,7 +232,9 @@ int64_t gsx_kmeans_workspace_bytes(int64_t n_total, int32_t nprob, int32_t K, in
  *   TENSOR_BF16    variant with split-bf16 operands (x = x1 + x2, three kind::f16 MMAs per K step, score error 2^-16
  *                  instead of 2^-9, so ~0.2 % instead of ~9 % of the points need a strict evaluation) and a single-pass
  *                  packed-key top-2 epilogue; measured slower than TENSOR on B200 (the top-2 costs more ALU work than
- *                  it saves in TMEM reads, profiles/r02_km_tc16_ncu.json) -- kept for A/B
+ *                  it saves in TMEM reads, profiles/r02_km_tc16_ncu.json).  A BUILD-TIME experiment: the shipped library
+ *                  returns GSX_ERR_UNSUPPORTED for it unless gsx_kmeans_tc.cu was compiled with -DGSX_KM_TC16=1
+ *                  (gsx_kmeans_tensor_core_supported reports bit 1 then)
  * tc_stats_dev (may be NULL): 3 uint64 counters accumulated by the TENSOR path {strict distance evaluations,
  * points with more than one candidate, points that needed the full strict scan}. */
 #define GSX_KM_ASSIGN_AUTO 0
@@ -243,6 +245,7 @@ int64_t gsx_kmeans_workspace_bytes(int64_t n_total, int32_t nprob, int32_t K, in
 int gsx_kmeans_lloyd_device(const float* X_dev, const int64_t* row_off_host, int32_t nprob, int32_t K, int32_t D,
                             int32_t max_iter, float* C_dev, int32_t* labels_dev, int32_t* counts_dev, void* ws,
                             int64_t ws_bytes, int32_t assign_mode, unsigned long long* tc_stats_dev, void* stream);
+/* 0: shape unsupported; bit 0: the TF32 kernel takes it; bit 1: the split-bf16 variant is compiled in */
 int32_t gsx_kmeans_tensor_core_supported(int32_t K, int32_t D);
 /* Test hook of the tensor-core assign: raw scores s[r][c] = x_r.c - ||c||^2/2 of the first min(rows,128) rows
  * against the K centroids, scores_dev float32[128 * roundup32(K)].  ws >= 1024 bytes. */

@@ -20,6 +20,8 @@ def _check(X, k, it, cuda, mode, seed=1234):
     Co, Lo, cnto = oracle.kmeans_lloyd(X, k, it, init=init)
     if mode.startswith("tensor") and not gk.tensor_core_supported(k, X.shape[1]):
         pytest.skip("shape not supported by the tensor-core path")
+    if mode == "tensor_bf16" and not gk.tensor_bf16_built():
+        pytest.skip("split-bf16 variant not compiled in (build-time experiment, -DGSX_KM_TC16=1)")
     C, L, cnt = gk.kmeans_lloyd(torch.from_numpy(X).to(cuda), k, it, torch.from_numpy(init).to(cuda), assign=mode)
     assert np.array_equal(L.cpu().numpy(), Lo)
     assert np.array_equal(cnt.cpu().numpy(), cnto)

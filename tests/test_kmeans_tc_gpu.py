@@ -21,6 +21,8 @@ def test_tc_scores_are_the_gemm(D, K, variant, rel, cuda, gsx_lib):
     rng = np.random.default_rng(D * 1000 + K)
     X = rng.normal(0, 0.15, (128, D)).astype(np.float32)
     C = rng.normal(0, 0.15, (K, D)).astype(np.float32)
+    if variant == 2 and not gk.tensor_bf16_built():
+        pytest.skip("split-bf16 variant not compiled in (build-time experiment, -DGSX_KM_TC16=1)")
     S = gk.tc_debug_scores(torch.from_numpy(X).to(cuda), torch.from_numpy(C).to(cuda), variant).cpu().numpy()[:, :K]
     exact = X.astype(np.float64) @ C.astype(np.float64).T - 0.5 * (C.astype(np.float64) ** 2).sum(1)[None]
     bound = rel * (np.linalg.norm(X, axis=1)[:, None] * np.linalg.norm(C, axis=1)[None] + 0.5 * (C ** 2).sum(1)[None]) + 1e-7
@@ -51,6 +53,8 @@ def test_tc_bf16_variant_margin_is_tight(cuda, gsx_lib):
     """Split-bf16 scores: the 100x tighter margin leaves < 2 % of the points with more than one candidate."""
     import torch
     from gsx import kmeans as gk
+    if not gk.tensor_bf16_built():
+        pytest.skip("split-bf16 variant not compiled in (build-time experiment, -DGSX_KM_TC16=1)")
     n, D, K = 400_000, 45, 256
     g = torch.Generator(device=cuda).manual_seed(9)
     proto = torch.randn(1024, D, device=cuda, generator=g) * 0.15
@@ -74,11 +78,12 @@ def test_tc_all_chunks_deterministic_and_equal_to_strict(cuda, gsx_lib):
         0.03 * torch.randn(nprob * rows, D, device=cuda, generator=g)
     offs = [p * rows for p in range(nprob + 1)]
     init = torch.stack([X[offs[p]:offs[p] + K] for p in range(nprob)])
-    runs = {m: gk.kmeans_lloyd_batched(X, offs, K, 3, init, assign=m) for m in ("tensor", "strict", "fma", "tensor_bf16")}
+    others = ("strict", "fma", "tensor_bf16") if gk.tensor_bf16_built() else ("strict", "fma")
+    runs = {m: gk.kmeans_lloyd_batched(X, offs, K, 3, init, assign=m) for m in ("tensor",) + others}
     again = gk.kmeans_lloyd_batched(X, offs, K, 3, init, assign="tensor")
     for a, b in zip(runs["tensor"], again):
         assert torch.equal(a, b)
-    for m in ("strict", "fma", "tensor_bf16"):
+    for m in others:
         assert torch.equal(runs["tensor"][1], runs[m][1])
         assert torch.equal(runs["tensor"][0].view(torch.int32), runs[m][0].view(torch.int32))
         assert torch.equal(runs["tensor"][2], runs[m][2])
