@@ -53,6 +53,13 @@ def test_morton_order_matches_reference_algorithm(n, kind, cuda, gsx_lib):
     import torch
     from gsx import morton, synth
     xyz = synth.xyz(n, kind)
+    if n >= 200_000:
+        # three blobs far tighter than a 1/1024 cell of the cloud's box: > 256 splats share a top-level code, so the
+        # reference recurses into them (twice for the tightest one)
+        rng = np.random.default_rng(n)
+        for start, cnt, sigma in ((1000, 400, 1e-3), (50_000, 1500, 1e-4), (120_000, 300, 1e-3)):
+            xyz[start:start + cnt] = xyz[start] + rng.normal(0, sigma, (cnt, 3)).astype(np.float32)
+        xyz[50_000:50_000 + 600] = xyz[50_000] + rng.normal(0, 1e-6, (600, 3)).astype(np.float32)
     want, _ = _morton_ref(xyz, "stable")
     got, levels = morton.morton_order(torch.from_numpy(xyz).to(cuda), return_levels=True)
     got = got.cpu().numpy().astype(np.int64)

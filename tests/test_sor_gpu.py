@@ -86,11 +86,16 @@ def test_mean_std_matches_numpy(cuda, gsx_lib):
     import torch
     from gsx import sor
     rng = np.random.default_rng(11)
-    for n in (1, 5, 8, 9, 27, 100, 128, 129, 1000, 4097, 100_003, 3_000_001):
+    for n in (1, 5, 8, 9, 27, 100, 128, 129, 1000, 4097, 100_003, 3_000_001, 16_777_216 + 5):
         a = rng.gamma(2.0, 0.3, n).astype(np.float32)
-        got = sor.mean_std(torch.from_numpy(a).to(cuda)).cpu().numpy()
         want = np.array([np.mean(a), np.std(a)], dtype=np.float32)
-        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), n
+        # 16-byte aligned vector: two lanes per leaf with float4 loads; offset by one element: the 8-lanes-per-leaf kernel
+        for shift in (0, 1):
+            buf = torch.empty(n + 4, dtype=torch.float32, device=cuda)
+            dev = buf[shift: shift + n]
+            dev.copy_(torch.from_numpy(a))
+            got = sor.mean_std(dev).cpu().numpy()
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (n, shift)
 
 
 @pytest.mark.parametrize("cell_scale", [1.0, 0.25])
