@@ -221,7 +221,10 @@ __global__ void __launch_bounds__(1024) k_pw_top(int64_t n, int dmax, int dtop, 
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        float v = __fdiv_rn(slot[0], __ll2float_rn((long long)n));
+        // NumPy divides the float32 sum by the element COUNT (an intp scalar): float32 / int64 promotes to float64, and the
+        // quotient is then rounded to float32 (_methods.py: ret.dtype.type(ret / rcount), true_divide(..., casting='unsafe')).
+        // Up to 2^24 elements that equals the float32 division; beyond, float32(n) is no longer n and it does not.
+        float v = __double2float_rn(__ddiv_rn((double)slot[0], (double)n));
         if (SQ) out[1] = __fsqrt_rn(v);
         else out[0] = v;
     }

@@ -158,13 +158,15 @@ static double pairwise_sum_f64(const double *a, int64_t n) {
 /* np.mean / np.std of a float32 vector (float32 accumulators), SURVEY A.1 step 9.
  * out[0] = mean, out[1] = std. */
 void orc_mean_std_f32(const float *a, int64_t n, float *out) {
-    float mean = orc_pairwise_sum_f32(a, n) / (float)n;
+    /* the float32 sum divided by the element count: NumPy promotes float32 / intp to float64 and rounds the quotient
+     * back to float32 (numpy/_core/_methods.py _mean / _var); identical to a float32 division only while n <= 2^24 */
+    float mean = (float)((double)orc_pairwise_sum_f32(a, n) / (double)n);
     float *x = (float *)malloc((size_t)(n > 0 ? n : 1) * sizeof(float));
     for (int64_t i = 0; i < n; ++i) {
         float t = a[i] - mean;
         x[i] = t * t;
     }
-    float var = orc_pairwise_sum_f32(x, n) / (float)n;
+    float var = (float)((double)orc_pairwise_sum_f32(x, n) / (double)n);
     free(x);
     out[0] = mean;
     out[1] = sqrtf(var);

@@ -13,7 +13,7 @@ import oracle
 
 
 @pytest.mark.parametrize("n", [1, 2, 5, 7, 8, 9, 15, 16, 27, 100, 127, 128, 129, 136, 255, 256, 257, 1000, 4097,
-                               8191, 100_003, 1_000_000, 3_000_001])
+                               8191, 100_003, 1_000_000, 3_000_001, 16_777_216 + 5, 20_000_003])
 def test_pairwise_mean_std_bit_exact(n):
     rng = np.random.default_rng(n)
     a = rng.gamma(2.0, 0.3, n).astype(np.float32)
