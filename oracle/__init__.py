@@ -4,11 +4,16 @@ Only tests/, ``__graft_entry__.smoke()`` and bench.py's ``cpu_baseline`` /
 ``--impl reference`` legs may import this package, and only as the checker.
 The product (``3dgsconverter_b200/``) never imports it.
 
-Parity status: **parity unpinned** by the reference (it has no tests or golden
-vectors; its Taichi kernels cannot run here).  What *is* pinned:
-the NumPy-visible arithmetic (pairwise mean/std, promotion rules) against NumPy
-itself, and the pure-NumPy reference filters (density / alpha / bbox / cKDTree
-SOR arithmetic) against the imported reference -- see tests/golden/make_goldens.py.
+Parity status.  The reference ships no tests or golden vectors and the real taichi wheel
+cannot be installed here, so nothing below was ever compared with a Taichi RUN.  What is pinned, and to what:
+  * Taichi-semantics SOR and Lloyd K-Means: to outputs of the reference's OWN kernel source --
+    /root/reference/gsconverter/processing/gpu_ops.py executed unmodified under a serial stand-in for the
+    `taichi` module (tests/golden/ti_serial.py, assumptions T1-T5 stated there: i32/f32 defaults, wrapping
+    i32 products, strict IEEE per operation, serial atomics) -> tests/golden/g4_reference_kernels.npz
+    (11 SOR runs on 8 clouds <= 3000 points, 4 K-Means problems), tests/test_reference_kernels_pin.py.
+    Larger sizes rest on this restatement plus the survey's anchor counts: "parity unpinned" beyond 3000 points.
+  * density / alpha / bbox / cKDTree SOR arithmetic: to the imported reference (tests/golden/make_goldens.py);
+  * NumPy-visible arithmetic (pairwise mean/std, promotion rules): to NumPy itself (tests/test_oracle_pins.py).
 """
 from __future__ import annotations
 

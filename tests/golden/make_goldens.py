@@ -6,9 +6,10 @@ What pins what:
   * density / alpha / bbox masks and the cKDTree-SOR mean distances come from the IMPORTED
     reference itself (/root/reference, with a stub `plyfile` module -- SURVEY §8c); the script asserts
     that oracle/ reproduces them exactly before writing.
-  * the Taichi-semantics SOR and the Lloyd K-Means cannot be executed from the reference (taichi is
-    not installable): their goldens are oracle outputs ("parity unpinned" by the reference), cross-checked
-    against the anchor counts of SURVEY §8(c), which were produced by an independent numba restatement.
+  * the Taichi-semantics SOR and the Lloyd K-Means at THESE sizes are oracle outputs (taichi is not installable;
+    cross-checked against the anchor counts of SURVEY §8(c), produced by an independent numba restatement).  The
+    oracle itself is pinned to the reference's kernel source on small clouds by make_taichi_goldens.py
+    (serial `taichi` stand-in, g4_reference_kernels.npz).
 Large arrays are stored as SHA-256 digests plus head/tail samples to keep the fixtures small.
 """
 import hashlib

@@ -1,0 +1,150 @@
+"""The pin for the Taichi-semantics SOR and the Lloyd K-Means: outputs of the REFERENCE'S OWN kernel source.
+
+tests/golden/g4_reference_kernels.npz was produced by executing /root/reference/gsconverter/processing/gpu_ops.py
+(unmodified: filter_sor_gpu :193-263 with kernel :98-176, _kmeans_taichi :178-191 with kernels :57-96) under the
+serial `taichi` stand-in of tests/golden/ti_serial.py (assumptions T1-T5 in its header), by
+tests/golden/make_taichi_goldens.py.  Bar: mean distances, keep-masks, labels and centroids bit-identical.
+
+  * CPU (`-m "not gpu"`): the oracle against the fixture; the stand-in really runs the reference's text (live, when
+    /root/reference exists -- it does not on the GPU box);
+  * GPU (`-m gpu`): the CUDA path, through the C ABI and through the drop-in plugin functions, against the fixture.
+"""
+import os
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+GOLD = Path(__file__).resolve().parent / "golden" / "g4_reference_kernels.npz"
+REF = "/root/reference/gsconverter/processing/gpu_ops.py"
+
+
+def _sor_cases(g):
+    for key in g.files:
+        if key.startswith("sor_") and key.endswith("_means"):
+            stem = key[: -len("_means")]
+            name, kpart, spart = stem[4:].rsplit("_", 2)
+            yield name, int(kpart[1:]), float(spart[1:]), g[f"sor_{name}_xyz"], g[key], g[stem + "_mask"]
+
+
+def _km_cases(g):
+    for key in g.files:
+        if key.startswith("km_") and key.endswith("_meta"):
+            name = key[3:-5]
+            K, iters, seed = (int(v) for v in g[key])
+            yield (name, g[f"km_{name}_X"], K, iters, seed, g[f"km_{name}_init_rows"], g[f"km_{name}_centroids"],
+                   g[f"km_{name}_labels"])
+
+
+def test_fixture_covers_the_reference_branches():
+    g = np.load(GOLD)
+    sor = {(n, k) for n, k, *_ in _sor_cases(g)}
+    assert len(sor) == 11 and ("mixed3k", 80) in sor and ("identical64", 16) in sor and ("tiny5", 16) in sor
+    km = {c[0]: c for c in _km_cases(g)}
+    assert set(km) == {"sh45", "dups3", "codebook1d", "lattice"}
+    # the duplicate-init case really leaves a cluster empty -> centroid row of zeros (gpu_ops.py:78-96)
+    name, X, K, iters, seed, rows, C, L = km["dups3"]
+    assert len(np.unique(X[rows], axis=0)) < K
+    empty = np.setdiff1d(np.arange(K), np.unique(L))
+    assert len(empty) >= 1 and not C[empty].any()
+
+
+def test_oracle_reproduces_reference_sor_kernel():
+    import oracle
+    g = np.load(GOLD)
+    n_cases = 0
+    for name, k, sigma, xyz, means, mask in _sor_cases(g):
+        got = oracle.sor_taichi_mean_dists(xyz, k, "i32wrap")
+        assert np.array_equal(got.view(np.uint32), means.view(np.uint32)), (name, k)
+        assert np.array_equal(oracle.threshold_mask(got, sigma), mask), (name, k)
+        n_cases += 1
+    assert n_cases == 11
+    # the elongated cloud separates the two readings of the probe hash: int32-wrapping (T1) is what the reference's
+    # source gives under the stand-in; the i64 reading differs on most points
+    xyz = g["sor_elongated_i32wrap_xyz"]
+    a = oracle.sor_taichi_mean_dists(xyz, 16, "i64")
+    assert (a.view(np.uint32) != g["sor_elongated_i32wrap_k16_s2.0_means"].view(np.uint32)).sum() > 1000
+
+
+def test_oracle_reproduces_reference_kmeans_kernels():
+    import oracle
+    g = np.load(GOLD)
+    for name, X, K, iters, seed, rows, C, L in _km_cases(g):
+        np.random.seed(seed)
+        assert np.array_equal(np.random.choice(len(X), K, replace=False), rows)   # the reference's draw (gpu_ops.py:182)
+        Co, Lo, cnt = oracle.kmeans_lloyd(X, K, iters, init=X[rows])
+        assert np.array_equal(Lo, L), name
+        assert np.array_equal(Co.view(np.uint32), C.view(np.uint32)), name
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="needs /root/reference (build container only)")
+def test_stand_in_executes_the_reference_source_live():
+    """A small live run: the reference's file, loaded by path with the stand-in, against the oracle; and the text the
+    stand-in compiled is the reference's kernel body (typed literals aside)."""
+    import sys
+    sys.path.insert(0, str(GOLD.parent))
+    import ti_serial
+    import oracle
+    ref = ti_serial.import_reference_gpu_ops()
+    src = ref.sor_compute_mean_dists.__ti_serial_source__
+    for fragment in ("h = (nx * p1 ^ ny * p2 ^ nz * p3) % hash_size", "while ins_pos >", "d = ti.sqrt(d2)",
+                     "mean_dists[i] = sum_d / _ti_f32cast(valid_k)"):
+        assert fragment in src, fragment
+    assert "centroids[l, dim] += data[i, dim]" in ref.k_means_update.__ti_serial_source__   # ti.atomic_add, serial (T4)
+    rng = np.random.default_rng(3)
+    xyz = np.concatenate([rng.normal(0, 0.05, (250, 3)), rng.uniform(-2, 2, (150, 3))]).astype(np.float32)
+    mask = ref.filter_sor_gpu(xyz, k=12, threshold_factor=1.5)
+    assert np.array_equal(mask, oracle.sor_taichi_mask(xyz, 12, 1.5, "i32wrap"))
+    X = rng.normal(size=(300, 5)).astype(np.float32)
+    np.random.seed(11)
+    C, L = ref._kmeans_taichi(X, 7, max_iter=3)
+    np.random.seed(11)
+    Co, Lo, _ = oracle.kmeans_lloyd(X, 7, 3, init=X[np.random.choice(300, 7, replace=False)])
+    assert np.array_equal(L, Lo) and np.array_equal(C.view(np.uint32), Co.view(np.uint32))
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+def test_cuda_sor_matches_reference_kernel_outputs(cuda, gsx_lib):
+    import torch
+    from gsx import sor
+    g = np.load(GOLD)
+    for name, k, sigma, xyz, means, mask in _sor_cases(g):
+        m, md = sor.sor_filter(torch.from_numpy(xyz).to(cuda), k, sigma, hash_mode="i32wrap", return_means=True)
+        assert np.array_equal(md.cpu().numpy().view(np.uint32), means.view(np.uint32)), (name, k)
+        assert np.array_equal(m.cpu().numpy(), mask), (name, k)
+
+
+@pytest.mark.gpu
+def test_plugin_filter_sor_gpu_matches_reference_outputs(cuda, gsx_lib):
+    """The function the reference's call site binds (data_processor.py:139 -> gpu_ops.filter_sor_gpu), host buffers."""
+    from gsconverter.processing import gpu_ops
+    g = np.load(GOLD)
+    for name, k, sigma, xyz, means, mask in _sor_cases(g):
+        got = gpu_ops.filter_sor_gpu(xyz.copy(), k=k, threshold_factor=sigma)
+        assert got.dtype == bool and np.array_equal(got, mask), (name, k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("assign", ["strict", "auto"])
+def test_cuda_kmeans_matches_reference_kernel_outputs(assign, cuda, gsx_lib):
+    import torch
+    from gsx import kmeans as gk
+    g = np.load(GOLD)
+    for name, X, K, iters, seed, rows, C, L in _km_cases(g):
+        Cg, Lg, cnt = gk.kmeans_lloyd(torch.from_numpy(X).to(cuda), K, iters, init=torch.from_numpy(X[rows]).to(cuda),
+                                      assign=assign)
+        assert np.array_equal(Lg.cpu().numpy(), L), (name, assign)
+        assert np.array_equal(Cg.cpu().numpy().view(np.uint32), C.view(np.uint32)), (name, assign)
+
+
+@pytest.mark.gpu
+def test_plugin_kmeans_matches_reference_outputs(cuda, gsx_lib):
+    """gpu_ops.kmeans(numpy) with the global NumPy RNG seeded as in the generator: same draw, same result."""
+    from gsconverter.processing import gpu_ops
+    g = np.load(GOLD)
+    for name, X, K, iters, seed, rows, C, L in _km_cases(g):
+        np.random.seed(seed)
+        Cg, Lg = gpu_ops.kmeans(X.copy(), K, max_iter=iters)
+        assert Lg.dtype == np.int32 and np.array_equal(Lg, L), name
+        assert np.array_equal(Cg.view(np.uint32), C.view(np.uint32)), name
