@@ -7,6 +7,7 @@
 #include "gsx_common.cuh"
 #include "gsx_compact.cuh"
 #include "gsx_density.cuh"
+#include "gsx_hostcopy.cuh"
 #include "gsx_kmeans.cuh"
 #include "gsx_knn_exact.cuh"
 #include "gsx_masks.cuh"
@@ -89,6 +90,7 @@ extern "C" {
 
 const char* gsx_last_error(void) { return g_err; }
 int gsx_version(void) { return 100; }
+const char* gsx_build_info(void) { return sor_build_info(); }
 long long gsx_kernel_launches(void) { return g_launches.load(); }
 int gsx_device_sm_count(void) {
     int dev = 0, v = 0;
@@ -284,12 +286,12 @@ int gsx_sor_filter_host(const float* xyz_host, int64_t n, int32_t k, float thres
     if ((rc = ws.alloc((size_t)wsb))) return rc;
     if ((rc = mask.alloc((size_t)n))) return rc;
     if ((rc = means.alloc((size_t)n * 4))) return rc;
-    GSX_CUDA_CHECK(cudaMemcpyAsync(xyz.p, xyz_host, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+    if ((rc = copy_h2d(xyz.p, xyz_host, (size_t)n * 12, st))) return rc;
     if ((rc = gsx_sor_filter_device((const float*)xyz.p, n, k, threshold_factor, hash_mode, (uint8_t*)mask.p,
                                     (float*)means.p, ws.p, wsb, st)))
         return rc;
-    GSX_CUDA_CHECK(cudaMemcpyAsync(mask_host, mask.p, (size_t)n, cudaMemcpyDeviceToHost, st));
-    if (means_host) GSX_CUDA_CHECK(cudaMemcpyAsync(means_host, means.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if ((rc = copy_d2h(mask_host, mask.p, (size_t)n, st))) return rc;
+    if (means_host && (rc = copy_d2h(means_host, means.p, (size_t)n * 4, st))) return rc;
     GSX_CUDA_CHECK(cudaStreamSynchronize(st));
     return GSX_OK;
 }
@@ -345,13 +347,13 @@ int gsx_sor_ckdtree_filter_host(const float* xyz_host, int64_t n, int32_t k, flo
     if ((rc = means.alloc((size_t)n * 4))) return rc;
     if ((rc = ms.alloc(64))) return rc;
     if ((rc = msws.alloc((size_t)msb))) return rc;
-    GSX_CUDA_CHECK(cudaMemcpyAsync(xyz.p, xyz_host, (size_t)n * 12, cudaMemcpyHostToDevice, st));
+    if ((rc = copy_h2d(xyz.p, xyz_host, (size_t)n * 12, st))) return rc;
     if ((rc = knn_exact_mean_dists((const float*)xyz.p, n, k, (float*)means.p, ws.p, wsb, st))) return rc;
     if ((rc = mean_std_f32((const float*)means.p, n, (float*)ms.p, msws.p, (size_t)msb, st))) return rc;
     if ((rc = threshold_mask((const float*)means.p, n, (const float*)ms.p, threshold_factor, (uint8_t*)mask.p, st)))
         return rc;
-    GSX_CUDA_CHECK(cudaMemcpyAsync(mask_host, mask.p, (size_t)n, cudaMemcpyDeviceToHost, st));
-    if (means_host) GSX_CUDA_CHECK(cudaMemcpyAsync(means_host, means.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if ((rc = copy_d2h(mask_host, mask.p, (size_t)n, st))) return rc;
+    if (means_host && (rc = copy_d2h(means_host, means.p, (size_t)n * 4, st))) return rc;
     GSX_CUDA_CHECK(cudaStreamSynchronize(st));
     return GSX_OK;
 }
@@ -466,14 +468,14 @@ int gsx_kmeans_host(const float* X_host, int64_t n, int32_t K, int32_t D, int32_
     if ((rc = L.alloc((size_t)n * 4))) return rc;
     if ((rc = cnt.alloc((size_t)K * 4))) return rc;
     if ((rc = ws.alloc((size_t)wsb))) return rc;
-    GSX_CUDA_CHECK(cudaMemcpyAsync(X.p, X_host, (size_t)n * D * 4, cudaMemcpyHostToDevice, st));
+    if ((rc = copy_h2d(X.p, X_host, (size_t)n * D * 4, st))) return rc;
     GSX_CUDA_CHECK(cudaMemcpyAsync(C.p, C_host_inout, (size_t)K * D * 4, cudaMemcpyHostToDevice, st));
     GSX_CUDA_CHECK(cudaMemsetAsync(L.p, 0, (size_t)n * 4, st));
     int64_t off[2] = {0, n};
     if ((rc = kmeans_lloyd((const float*)X.p, off, 1, K, D, max_iter, (float*)C.p, (int*)L.p, (int*)cnt.p, ws.p, wsb, assign_mode, nullptr, st)))
         return rc;
     GSX_CUDA_CHECK(cudaMemcpyAsync(C_host_inout, C.p, (size_t)K * D * 4, cudaMemcpyDeviceToHost, st));
-    GSX_CUDA_CHECK(cudaMemcpyAsync(labels_host, L.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if ((rc = copy_d2h(labels_host, L.p, (size_t)n * 4, st))) return rc;
     GSX_CUDA_CHECK(cudaStreamSynchronize(st));
     return GSX_OK;
 }
@@ -495,16 +497,26 @@ int gsx_kmeans_host_batched(const float* X_host, const int64_t* row_off_host, in
     if ((rc = L.alloc((size_t)n * 4))) return rc;
     if ((rc = cnt.alloc((size_t)nprob * K * 4))) return rc;
     if ((rc = ws.alloc((size_t)wsb))) return rc;
-    GSX_CUDA_CHECK(cudaMemcpyAsync(X.p, X_host, (size_t)n * D * 4, cudaMemcpyHostToDevice, st));
+    if ((rc = copy_h2d(X.p, X_host, (size_t)n * D * 4, st))) return rc;
     GSX_CUDA_CHECK(cudaMemcpyAsync(C.p, C_host_inout, (size_t)nprob * K * D * 4, cudaMemcpyHostToDevice, st));
     GSX_CUDA_CHECK(cudaMemsetAsync(L.p, 0, (size_t)n * 4, st));
     if ((rc = kmeans_lloyd((const float*)X.p, row_off_host, nprob, K, D, max_iter, (float*)C.p, (int*)L.p, (int*)cnt.p,
                            ws.p, wsb, assign_mode, nullptr, st)))
         return rc;
     GSX_CUDA_CHECK(cudaMemcpyAsync(C_host_inout, C.p, (size_t)nprob * K * D * 4, cudaMemcpyDeviceToHost, st));
-    GSX_CUDA_CHECK(cudaMemcpyAsync(labels_host, L.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    if ((rc = copy_d2h(labels_host, L.p, (size_t)n * 4, st))) return rc;
     GSX_CUDA_CHECK(cudaStreamSynchronize(st));
     return GSX_OK;
+}
+
+/* ------------------------------------------------------------------ pageable host buffers <-> HBM */
+int gsx_copy_h2d(void* dst_dev, const void* src_host, int64_t bytes, void* stream) {
+    GSX_REQUIRE(bytes >= 0 && (bytes == 0 || (dst_dev && src_host)), GSX_ERR_ARG, "copy_h2d: bad arguments");
+    return copy_h2d(dst_dev, src_host, (size_t)bytes, (cudaStream_t)stream);
+}
+int gsx_copy_d2h(void* dst_host, const void* src_dev, int64_t bytes, void* stream) {
+    GSX_REQUIRE(bytes >= 0 && (bytes == 0 || (dst_host && src_dev)), GSX_ERR_ARG, "copy_d2h: bad arguments");
+    return copy_d2h(dst_host, src_dev, (size_t)bytes, (cudaStream_t)stream);
 }
 
 /* ------------------------------------------------------------------ device-resident records (SURVEY 8f 2,4) */

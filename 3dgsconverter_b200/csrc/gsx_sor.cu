@@ -947,6 +947,15 @@ __device__ __forceinline__ float warp_sort32(float v, int lane) {
     return v;
 }
 
+#ifndef GSX_KNN_FIRST_SORT
+#define GSX_KNN_FIRST_SORT 1
+#endif
+// Epilogue of a query (gpu_ops.py:163-174: serial float32 sum of the valid distances, mean) -- batched: every query
+// of a batch parks its K ascending distances and its row number in shared memory, and after the batch lane q sums
+// query q (16 serial sums run side by side instead of one shuffle + add per rank on lane 0 of every query).
+#ifndef GSX_KNN_EPI_SMEM
+#define GSX_KNN_EPI_SMEM 1
+#endif
 template <int NREG>
 struct TopK {
     float v0, v1;  // lane l holds rank l (v0) and rank 32+l (v1) of the ascending d^2 list
@@ -978,6 +987,15 @@ struct TopK {
     // >= rank K-1, so they never change the K smallest (only the multiset of values matters, A.1-7).
     __device__ __forceinline__ void merge32(float nv, int lane) {
         nv = warp_sort32(nv, lane);
+#if GSX_KNN_FIRST_SORT
+        // the first merge of a query meets an empty list (32 sentinels): the sorted candidates ARE the merged list --
+        // skips the reversal and the 5 merge stages (the sentinel is the largest value either side can hold)
+        if (__all_sync(GSX_FULL, v0 == __uint_as_float(GSX_D2LIM_BITS))) {
+            v0 = nv;
+            refresh_tau();
+            return;
+        }
+#endif
         float r = __shfl_sync(GSX_FULL, nv, 31 - lane);
         float m = fminf(v0, r);
 #pragma unroll
@@ -1036,7 +1054,7 @@ __device__ __forceinline__ void scan32(const float4* __restrict__ spos, pos_t j,
 #ifndef GSX_KNN_MINBLOCKS
 #define GSX_KNN_MINBLOCKS 8
 #endif
-template <int NREG, bool STATS>
+template <int NREG, bool STATS, int ES>
 __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
     k_sor_knn(const float4* __restrict__ spos, const int2* __restrict__ tab_se, const float4* __restrict__ tab_box,
               const uint32_t* __restrict__ cellbits, const float4* __restrict__ caabb,
@@ -1046,6 +1064,10 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
               uint32_t n, uint64_t M, unsigned long long* __restrict__ stats) {
     const int lane = lane_id();
     unsigned long long st_visits = 0, st_scanned = 0, st_boxes = 0, st_queries = 0;
+    // batched epilogue (ES > 0): [8 warps][kQueryBatch][ES] floats, a row = ES-1 ranks (>= K) + the row number; ES is
+    // odd so that the lanes of the final pass (one query each) read distinct banks
+    extern __shared__ float s_epi[];
+    float* const epi = s_epi + (threadIdx.x >> 5) * (kQueryBatch * (ES > 0 ? ES : 1));
 #if GSX_KNN_TMA
     __shared__ __align__(128) float4 s_stage[8][kSmallBucket];
     __shared__ __align__(8) unsigned long long s_bar[8];
@@ -1082,12 +1104,13 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
 #endif
         int ps = 0, pc = 0;                                  // lane p: bucket range of probe p
         float blx = 0.f, bly = 0.f, blz = 0.f, bhx = 0.f, bhy = 0.f, bhz = 0.f;  // and its bounding box
+        const pos_t qb_p = (pos_t)qb, qe_p = (pos_t)qe;      // positions fit 31 bits (pos_t): 32-bit loop bookkeeping
 #pragma unroll 1
-        for (int64_t i = qb; i < qe; ++i) {
+        for (pos_t i = qb_p; i < qe_p; ++i) {
             const float4 q = __ldg(spos + i);
 #if GSX_KNN_CELLBITS
-            const uint32_t w_i = (i >> 5) == (qb >> 5) ? cellword : __ldg(cellbits + (i >> 5));
-            if (i == qb || ((w_i >> (i & 31)) & 1u)) {   // warp-uniform by construction
+            const uint32_t w_i = (i >> 5) == (qb_p >> 5) ? cellword : __ldg(cellbits + (i >> 5));
+            if (i == qb_p || ((w_i >> (i & 31)) & 1u)) {   // warp-uniform by construction
                 const int gx = (int)floorf(__fdiv_rn(__fsub_rn(q.x, bx), cell));
                 const int gy = (int)floorf(__fdiv_rn(__fsub_rn(q.y, by), cell));
                 const int gz = (int)floorf(__fdiv_rn(__fsub_rn(q.z, bz), cell));
@@ -1173,7 +1196,7 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
             int skip_chunk = -1;
             {
                 int s13 = __shfl_sync(GSX_FULL, ps, 13), c13 = __shfl_sync(GSX_FULL, pc, 13);
-                if (c13 > kSmallBucket && i >= s13 && i < (int64_t)s13 + c13) {
+                if (c13 > kSmallBucket && i >= s13 && i < (pos_t)s13 + c13) {
                     skip_chunk = (int)(i >> 5);
                     const pos_t j = ((pos_t)skip_chunk << 5) + lane;
                     scan32<NREG, STATS>(spos, j, j >= s13 && j < (pos_t)s13 + c13, q.x, q.y, q.z, tk, lane,
@@ -1243,6 +1266,10 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
             // gpu_ops.py:163-174: ascending serial float32 sum of the valid (< 0.9e10) distances.  The
             // list is ascending, so the valid entries are a prefix of the first K ranks.
             const float d0 = __fsqrt_rn(tk.v0), d1 = NREG == 2 ? __fsqrt_rn(tk.v1) : 0.f;
+            if (ES > 0) {   // park the list: ranks 0..ES-2 (>= K of them) and the row number in the last slot
+                if (lane < ES) epi[(int)(i - qb_p) * ES + lane] = lane == ES - 1 ? q.w : d0;
+                continue;
+            }
             int valid = __popc(__ballot_sync(GSX_FULL, lane < K && d0 < 0.9e10f));
             if (NREG == 2) valid += __popc(__ballot_sync(GSX_FULL, lane + 32 < K && d1 < 0.9e10f));
             float sum = 0.f;
@@ -1251,6 +1278,23 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
                 sum = __fadd_rn(sum, x);
             }
             if (lane == 0) final_means[__float_as_int(q.w)] = valid > 0 ? __fdiv_rn(sum, (float)valid) : 0.f;
+        }
+        if (ES > 0) {
+            __syncwarp();
+            if (lane < (int)(qe - qb)) {   // lane q: the serial sum of query q, rank order, exactly as above
+                const float* row = epi + lane * ES;
+                float sum = 0.f;
+                int valid = 0;
+                for (int r = 0; r < K; ++r) {
+                    const float x = row[r];
+                    if (x < 0.9e10f) {
+                        sum = __fadd_rn(sum, x);
+                        ++valid;
+                    }
+                }
+                final_means[__float_as_int(row[ES - 1])] = valid > 0 ? __fdiv_rn(sum, (float)valid) : 0.f;
+            }
+            __syncwarp();   // the next batch overwrites the rows
         }
     }
     if (STATS && lane == 0) {
@@ -1261,6 +1305,10 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
     }
 }
 
+#ifndef GSX_KNN16
+#define GSX_KNN16 0   // 1: K <= 16 goes to the two-queries-per-warp kernel (gsx_sor_knn16.cuh) -- an A/B variant, it
+                      // measured SLOWER than the warp-per-query kernel (profiles/r02_knn16_variants.log)
+#endif
 #include "gsx_sor_knn16.cuh"
 
 __global__ void k_fill_f32(float* p, int64_t n, float v) {
@@ -1268,26 +1316,23 @@ __global__ void k_fill_f32(float* p, int64_t n, float v) {
     if (i < n) p[i] = v;
 }
 
-template <int NREG, bool STATS>
+template <int NREG, bool STATS, int ES>
 static int launch_knn(SorWs& w, int64_t q_begin, int64_t q_end, int q_stride, int q_phase, int K, int hash_mode,
                       const float* bmin, float cell,
                       float* final_means, unsigned long long* stats, uint64_t M, int64_t want, cudaStream_t st) {
     int per_sm = 0;
-    GSX_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sor_knn<NREG, STATS>, 256, 0));
+    const size_t smem = (size_t)8 * kQueryBatch * ES * sizeof(float);
+    GSX_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sor_knn<NREG, STATS, ES>, 256, smem));
     int64_t grid = (int64_t)sm_count() * (per_sm > 0 ? per_sm : 4);  // persistent: exactly the resident CTAs
     if (grid > want) grid = want;
     if (grid < 1) grid = 1;
-    k_sor_knn<NREG, STATS><<<(int)grid, 256, 0, st>>>(w.spos, w.tab_se, w.tab_box, w.cellbits, w.caabb, w.saabb, final_means, w.counters,
+    k_sor_knn<NREG, STATS, ES><<<(int)grid, 256, smem, st>>>(w.spos, w.tab_se, w.tab_box, w.cellbits, w.caabb, w.saabb, final_means, w.counters,
                                                       q_begin, q_end, q_stride, q_phase, K, hash_mode, bmin[0], bmin[1],
                                                       bmin[2], cell,
                                                       (uint32_t)w.n, M, stats);
     return GSX_OK;
 }
 
-#ifndef GSX_KNN16
-#define GSX_KNN16 0   // 1: K <= 16 goes to the two-queries-per-warp kernel (gsx_sor_knn16.cuh) -- an A/B variant, it
-                      // measured SLOWER than the warp-per-query kernel (profiles/r02_knn16_variants.log)
-#endif
 template <bool STATS>
 static int launch_knn16(SorWs& w, int64_t q_begin, int64_t q_end, int q_stride, int q_phase, int K, int hash_mode,
                         const float* bmin, float cell, float* final_means, unsigned long long* stats, uint64_t M,
@@ -1302,6 +1347,18 @@ static int launch_knn16(SorWs& w, int64_t q_begin, int64_t q_end, int q_stride, 
                                                   w.counters, q_begin, q_end, q_stride, q_phase, K, hash_mode, bmin[0],
                                                   bmin[1], bmin[2], cell, (uint32_t)w.n, M, stats);
     return GSX_OK;
+}
+
+// compile-time configuration of the query kernel (A/B variants differ only here): recorded next to every ncu capture
+// and checked by bench.py before it uses a capture's instruction count for the roofline
+#define GSX_STR2(x) #x
+#define GSX_STR(x) GSX_STR2(x)
+const char* sor_build_info() {
+    return "knn=r02c"
+           ";epi_smem=" GSX_STR(GSX_KNN_EPI_SMEM) ";first_sort=" GSX_STR(GSX_KNN_FIRST_SORT)
+           ";query_batch=" GSX_STR(GSX_QUERY_BATCH) ";minblocks=" GSX_STR(GSX_KNN_MINBLOCKS)
+           ";merge_threshold=" GSX_STR(GSX_MERGE_THRESHOLD) ";small_bucket=" GSX_STR(GSX_SMALL_BUCKET)
+           ";knn16=" GSX_STR(GSX_KNN16) ";tma=" GSX_STR(GSX_KNN_TMA) ";i32=" GSX_STR(GSX_KNN_I32);
 }
 
 int sor_mean_dists(SorWs& w, int64_t q_begin, int64_t q_end, int q_stride, int q_phase, int k, int hash_mode,
@@ -1329,10 +1386,15 @@ int sor_mean_dists(SorWs& w, int64_t q_begin, int64_t q_end, int q_stride, int q
     if (GSX_KNN16 && K <= 16)
         rc = stats ? launch_knn16<true>(w, q_begin, q_end, q_stride, q_phase, K, hash_mode, bmin, cell, final_means, stats, M, want, st)
                    : launch_knn16<false>(w, q_begin, q_end, q_stride, q_phase, K, hash_mode, bmin, cell, final_means, stats, M, want, st);
-    else if (stats) rc = K <= 32 ? launch_knn<1, true>(w, q_begin, q_end, q_stride, q_phase, K, hash_mode, bmin, cell, final_means, stats, M, want, st)
-                            : launch_knn<2, true>(w, q_begin, q_end, q_stride, q_phase, K, hash_mode, bmin, cell, final_means, stats, M, want, st);
-    else rc = K <= 32 ? launch_knn<1, false>(w, q_begin, q_end, q_stride, q_phase, K, hash_mode, bmin, cell, final_means, stats, M, want, st)
-                      : launch_knn<2, false>(w, q_begin, q_end, q_stride, q_phase, K, hash_mode, bmin, cell, final_means, stats, M, want, st);
+    else {
+#define GSX_KNN_ARGS w, q_begin, q_end, q_stride, q_phase, K, hash_mode, bmin, cell, final_means, stats, M, want, st
+        // ES = row stride of the batched shared-memory epilogue (0: per-query shuffle epilogue)
+        constexpr int ES16 = GSX_KNN_EPI_SMEM ? 17 : 0, ES32 = GSX_KNN_EPI_SMEM ? 33 : 0;
+        if (K <= 16) rc = stats ? launch_knn<1, true, ES16>(GSX_KNN_ARGS) : launch_knn<1, false, ES16>(GSX_KNN_ARGS);
+        else if (K <= 32) rc = stats ? launch_knn<1, true, ES32>(GSX_KNN_ARGS) : launch_knn<1, false, ES32>(GSX_KNN_ARGS);
+        else rc = stats ? launch_knn<2, true, 0>(GSX_KNN_ARGS) : launch_knn<2, false, 0>(GSX_KNN_ARGS);
+#undef GSX_KNN_ARGS
+    }
     if (rc) return rc;
     GSX_KERNEL_CHECK();
     return GSX_OK;

@@ -50,6 +50,8 @@ int sor_dist_merge(const float4* pos4_in, int64_t m, int64_t n_global, int64_t b
 int sor_build_from_sorted(const float4* spos_in, const uint8_t* flags, int64_t n, const float* bmin, float cell, SorWs& w,
                           cudaStream_t st);
 
+const char* sor_build_info();
+
 size_t mean_std_ws_bytes(int64_t n);
 int mean_std_f32(const float* a, int64_t n, float* out_dev, void* ws, size_t ws_bytes, cudaStream_t st);
 int64_t pairwise_slots(int64_t n);

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(256, GSX_KNN16_MINBLOCKS)
                 float* __restrict__ final_means, unsigned int* __restrict__ work, int64_t q_begin, int64_t q_end,
                 int q_stride, int q_phase, int K, int hash_mode, float bx, float by, float bz, float cell, uint32_t n,
                 uint64_t M, unsigned long long* __restrict__ stats) {
-    static_assert(kQueryBatch == 16, "a half-warp batch is one 16-position run");
+    static_assert(!GSX_KNN16 || kQueryBatch == 16, "a half-warp batch is one 16-position run");
     const int lane = lane_id();
     Lanes16 L;
     L.base = lane & 16;

@@ -32,6 +32,7 @@ _i32 = C.c_int32
 _SIGS = {
     "gsx_last_error": (C.c_char_p, []),
     "gsx_version": (C.c_int, []),
+    "gsx_build_info": (C.c_char_p, []),
     "gsx_device_sm_count": (C.c_int, []),
     "gsx_kernel_launches": (C.c_longlong, []),
     "gsx_sor_workspace_bytes": (_i64, [_i64]),
@@ -90,6 +91,8 @@ _SIGS = {
     "gsx_morton_order": (C.c_int, [_vp, _i64, _vp, _i32, C.POINTER(_i32), _vp, _i64, _vp]),
     "gsx_chunk_minmax": (C.c_int, [_vp, _i64, _i32, _vp, _i32, C.POINTER(_i32), _i32, C.c_float, C.c_float, _vp, _vp, _vp,
                                    _i64, _vp]),
+    "gsx_copy_h2d": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "gsx_copy_d2h": (C.c_int, [_vp, _vp, _i64, _vp]),
     "gsx_device_memory": (C.c_int, [C.POINTER(_i64), C.POINTER(_i64)]),
 }
 

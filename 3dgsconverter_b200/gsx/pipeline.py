@@ -35,8 +35,9 @@ def compact(mask: torch.Tensor, xyz: torch.Tensor, opacity: torch.Tensor | None,
 
 class FilterChain:
     def __init__(self, xyz, opacity=None, device="cuda"):
-        to_dev = lambda a: (a if isinstance(a, torch.Tensor) else torch.from_numpy(  # noqa: E731
-            np.ascontiguousarray(a, dtype=np.float32))).to(device)
+        from .hostcopy import to_device
+        to_dev = lambda a: (a.to(device) if isinstance(a, torch.Tensor) else  # noqa: E731
+                            to_device(np.ascontiguousarray(a, dtype=np.float32), device))
         self.xyz = to_dev(xyz).contiguous()
         self.opacity = to_dev(opacity).contiguous() if opacity is not None else None
         self.idx = None            # None == identity (nothing removed yet)
@@ -94,7 +95,8 @@ class FilterChain:
         """Surviving original row indices (ascending), on the host."""
         if self.idx is None:
             return np.arange(self.n0, dtype=np.int64)
-        return self.idx.cpu().numpy().astype(np.int64)
+        from .hostcopy import to_host
+        return to_host(self.idx).astype(np.int64)
 
     def rebase(self):
         """Declare the current survivors to be rows 0..count-1 of a freshly compacted host array."""

@@ -30,7 +30,8 @@ class DeviceRecords:
         if not is_packed_f32(a):
             raise ValueError("DeviceRecords needs a packed all-float32 structured array")
         flat = np.ascontiguousarray(a).view(np.float32).reshape(len(a), len(a.dtype.names))
-        return cls(torch.from_numpy(flat).to(device), a.dtype.names, a.dtype)
+        from .hostcopy import to_device
+        return cls(to_device(flat, device), a.dtype.names, a.dtype)
 
     def __len__(self):
         return self.rows.shape[0]
@@ -60,7 +61,8 @@ class DeviceRecords:
 
     def to_host(self) -> np.ndarray:
         """The structured array the writers consume (one D2H)."""
-        flat = self.rows.cpu().numpy()
+        from .hostcopy import to_host
+        flat = to_host(self.rows)
         return flat.reshape(-1).view(self.dtype)
 
     # ---- elementwise attribute transforms of the writers

@@ -417,13 +417,21 @@ def run_c2(args):
     issue_peak = 148 * 4 * sm_mhz * 1e6 / 1e9          # G warp-instructions / s: 148 SMs x 4 schedulers x clock
     alg_bytes = st["queries"] * (16 + 27 * 8 + 4) + 16 * st["scanned"] + 32 * (st["box_tests"] + st.get("box_loads", 0))
     ref_model_bytes = st["queries"] * (16 + 27 * 8 + 4) + 16 * st["visits"]
+    # the newest committed capture taken with THIS build of the query kernel (gsx_build_info) and this configuration
+    from gsx import _abi as _gabi
+    build_info = _gabi.lib.gsx_build_info().decode()
     prof = {}
-    try:
-        prof = json.loads((ROOT / "profiles" / "r02_knn_ncu.json").read_text())
-    except Exception:
-        pass
+    for cand in ("r02c_knn_ncu.json", "r02_knn_ncu.json"):
+        try:
+            c = json.loads((ROOT / "profiles" / cand).read_text())
+        except Exception:
+            continue
+        if c.get("build_info", "knn=r02") == build_info or (cand == "r02_knn_ncu.json" and not prof):
+            prof = dict(c, file=cand)
+            if c.get("build_info") == build_info:
+                break
     same_cfg = bool(prof) and world == 1 and n == prof.get("n") and args.kind == prof.get("kind") and \
-        args.hash == prof.get("hash")
+        args.hash == prof.get("hash") and prof.get("build_info") == build_info
     winst = prof.get("warp_instructions_per_launch") if same_cfg else None
     traffic = prof.get("dram_bytes_per_launch") if same_cfg else None
     kname = (prof.get("kernel") or "k_sor_knn16 (K<=16) / k_sor_knn").split("(const")[0].replace("void ", "").strip()
@@ -438,6 +446,7 @@ def run_c2(args):
                 "kernel_ms": round(knn_avg_ms, 3), "kernel_share_of_step": round(knn_avg_ms / ms_per_step, 3),
                 "warp_instr_per_query": round(winst / prof["queries"], 1) if winst else None,
                 "ncu_issue_active_pct": prof.get("issue_active_pct") if same_cfg else None,
+                "ncu_capture": prof.get("file") if same_cfg else None, "build_info": build_info,
                 "per_query": {"ref_visits_V": round(st["visits"] / st["queries"], 1),
                               "scanned": round(st["scanned"] / st["queries"], 1),
                               "box_tests": round(st["box_tests"] / st["queries"], 1)},

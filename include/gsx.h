@@ -37,6 +37,8 @@ extern "C" {
 /* ---- library ---------------------------------------------------------------------- */
 const char* gsx_last_error(void);
 int gsx_version(void);          /* 100*major + minor */
+const char* gsx_build_info(void); /* compile-time switches of the SOR query kernel ("knn=r02c;epi_smem=1;..."): names the
+                                   * build an ncu capture / a bench line was taken with */
 int gsx_device_sm_count(void);  /* SMs of the current device (grid sizing), <0 on error */
 long long gsx_kernel_launches(void); /* cumulative number of gsx kernels launched by this process */
 
@@ -298,6 +300,16 @@ int gsx_chunk_minmax(const float* rows_dev, int64_t n, int32_t F, const int32_t*
  * C_host_inout float32[nprob*K*D]: the init rows on entry, the centroids on return; labels_host int32[n]. */
 int gsx_kmeans_host_batched(const float* X_host, const int64_t* row_off_host, int32_t nprob, int32_t K, int32_t D,
                             int32_t max_iter, float* C_host_inout, int32_t* labels_host, int32_t assign_mode);
+/* Copies between a caller's HOST buffer and HBM, used by every *_host entry point above.  The reference's call sites
+ * pass ordinary (pageable) NumPy arrays -- np.column_stack at data_processor.py:139, the shN block of
+ * sog.py:536-549 -- which cudaMemcpy stages on one CPU thread at ~11 GB/s; these stage through a pool of pinned
+ * chunks filled / drained by several host threads (GSX_COPY_THREADS, default 8), each enqueueing its own DMAs, so
+ * the PCIe link stays busy.  Pinned / registered / managed buffers and copies below 8 MiB take plain
+ * cudaMemcpyAsync (GSX_STAGED_COPY=0 forces that path).
+ * gsx_copy_h2d: on return src_host has been read completely and `stream` is ordered after the last chunk.
+ * gsx_copy_d2h: waits for what `stream` has produced and BLOCKS until dst_host is complete. */
+int gsx_copy_h2d(void* dst_dev, const void* src_host, int64_t bytes, void* stream);
+int gsx_copy_d2h(void* dst_host, const void* src_dev, int64_t bytes, void* stream);
 /* Free / total memory of the current device, for the sizing decisions of the host-buffer callers. */
 int gsx_device_memory(int64_t* free_bytes, int64_t* total_bytes);
 
