@@ -15,6 +15,7 @@
 #include "gsx_sor.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 #include <vector>
 
 namespace gsx {
@@ -616,6 +617,57 @@ __global__ void __launch_bounds__(256) k_vox_member4(const float4* __restrict__ 
     mask4[t] = o;
 }
 
+// Bitmap form of the keep set: when the bounding box of the kept voxels is small (the usual case -- a few clusters of
+// voxels of one scene unit) one bit per voxel of that box replaces the hash probe: the whole set is a few KiB that stay
+// in L1, and the kernel streams at the speed of the bbox mask instead of waiting on dependent table reads.
+struct VoxBits {
+    long long ox, oy, oz;
+    unsigned long long dx, dy, dz;
+};
+
+__device__ __forceinline__ uint8_t vox_member_bit(float x, float y, float z, float voxel, const VoxBits& g,
+                                                  const uint32_t* __restrict__ bits) {
+    const unsigned long long rx = (unsigned long long)(voxel_of(x, voxel) - g.ox),
+                             ry = (unsigned long long)(voxel_of(y, voxel) - g.oy),
+                             rz = (unsigned long long)(voxel_of(z, voxel) - g.oz);
+    if (rx >= g.dx || ry >= g.dy || rz >= g.dz) return 0;    // (negative differences wrap to huge values)
+    const uint32_t idx = (uint32_t)((rx * g.dy + ry) * g.dz + rz);
+    return (uint8_t)((__ldg(bits + (idx >> 5)) >> (idx & 31u)) & 1u);
+}
+
+__global__ void __launch_bounds__(256) k_vox_member_bits(const float* __restrict__ xyz, int64_t begin, int64_t n,
+                                                         float voxel, VoxBits g, const uint32_t* __restrict__ bits,
+                                                         uint8_t* __restrict__ mask) {
+    int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    mask[i] = vox_member_bit(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], voxel, g, bits);
+}
+
+__global__ void __launch_bounds__(256) k_vox_member_bits4(const float4* __restrict__ xyz4, int64_t n4, float voxel,
+                                                          VoxBits g, const uint32_t* __restrict__ bits,
+                                                          uchar4* __restrict__ mask4) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n4) return;
+    float4 a = ld_stream_f4(xyz4 + 3 * t), b = ld_stream_f4(xyz4 + 3 * t + 1), c = ld_stream_f4(xyz4 + 3 * t + 2);
+    uchar4 o;
+    o.x = vox_member_bit(a.x, a.y, a.z, voxel, g, bits);
+    o.y = vox_member_bit(a.w, b.x, b.y, voxel, g, bits);
+    o.z = vox_member_bit(b.z, b.w, c.x, voxel, g, bits);
+    o.w = vox_member_bit(c.y, c.z, c.w, voxel, g, bits);
+    mask4[t] = o;
+}
+
+constexpr unsigned long long kMaxKeepBits = 1ull << 27;   // 16 MiB of bitmap at most; larger boxes use the hash set
+
+static bool keep_bitmap_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GSX_DENSITY_BITMAP");
+        v = !(e && e[0] == '0');
+    }
+    return v != 0;
+}
+
 int density_member_mask(const float* xyz, int64_t n, float voxel, const int64_t* keep, int64_t n_keep, uint8_t* mask,
                         void* ws, int64_t ws_bytes, cudaStream_t st) {
     GSX_NVTX("gsx::density_member_mask");
@@ -635,6 +687,41 @@ int density_member_mask(const float* xyz, int64_t n, float voxel, const int64_t*
     for (int a = 0; a < 3; ++a) {
         GSX_REQUIRE(hi[a] - o[a] < (1ll << 31), GSX_ERR_UNSUPPORTED, "density: kept voxels span more than 2^31 on axis %d", a);
         if (hi[a] - o[a] >= kAxisLim) wide = true;
+    }
+    {   // bitmap over the bounding box of the kept voxels, when that box is small enough
+        const unsigned long long dx = (unsigned long long)(hi[0] - o[0] + 1), dy = (unsigned long long)(hi[1] - o[1] + 1),
+                                 dz = (unsigned long long)(hi[2] - o[2] + 1);
+        // (each factor < 2^31: the products below cannot overflow before the comparisons reject them)
+        const bool small = dx <= kMaxKeepBits && dy <= kMaxKeepBits && dx * dy <= kMaxKeepBits &&
+                           dx * dy * dz <= kMaxKeepBits;
+        const size_t nwords = small ? (size_t)((dx * dy * dz + 31) / 32) : 0;
+        if (small && keep_bitmap_enabled() && nwords * 4 <= (size_t)ws_bytes) {
+            std::vector<uint32_t> bm(nwords, 0u);
+            for (int64_t t = 0; t < n_keep; ++t) {
+                const unsigned long long idx = ((unsigned long long)(keep[3 * t] - o[0]) * dy +
+                                                (unsigned long long)(keep[3 * t + 1] - o[1])) * dz +
+                                               (unsigned long long)(keep[3 * t + 2] - o[2]);
+                bm[idx >> 5] |= 1u << (idx & 31);
+            }
+            GSX_CUDA_CHECK(cudaMemcpyAsync(ws, bm.data(), nwords * 4, cudaMemcpyHostToDevice, st));
+            GSX_CUDA_CHECK(cudaStreamSynchronize(st));  // bm is a stack-owned pageable buffer
+            const VoxBits g{o[0], o[1], o[2], dx, dy, dz};
+            const uint32_t* bits = (const uint32_t*)ws;
+            int64_t n4 = 0;
+            if (((uintptr_t)xyz % 16 == 0) && ((uintptr_t)mask % 4 == 0)) {
+                n4 = n / 4;
+                if (n4 > 0) {
+                    k_vox_member_bits4<<<(int)((n4 + 255) / 256), 256, 0, st>>>((const float4*)xyz, n4, voxel, g, bits,
+                                                                               (uchar4*)mask);
+                    GSX_KERNEL_CHECK();
+                }
+            }
+            if (n - 4 * n4 > 0) {
+                k_vox_member_bits<<<(int)((n - 4 * n4 + 255) / 256), 256, 0, st>>>(xyz, 4 * n4, n, voxel, g, bits, mask);
+                GSX_KERNEL_CHECK();
+            }
+            return GSX_OK;
+        }
     }
     size_t slots = 64;
     while (slots < (size_t)2 * n_keep) slots <<= 1;

@@ -1064,6 +1064,7 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
               uint32_t n, uint64_t M, unsigned long long* __restrict__ stats) {
     const int lane = lane_id();
     unsigned long long st_visits = 0, st_scanned = 0, st_boxes = 0, st_queries = 0;
+    static_assert(ES >= 0 && ES <= 33, "a row holds at most the 32 ranks of one register + the row number");
     // batched epilogue (ES > 0): [8 warps][kQueryBatch][ES] floats, a row = ES-1 ranks (>= K) + the row number; ES is
     // odd so that the lanes of the final pass (one query each) read distinct banks
     extern __shared__ float s_epi[];
@@ -1267,7 +1268,13 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
             // list is ascending, so the valid entries are a prefix of the first K ranks.
             const float d0 = __fsqrt_rn(tk.v0), d1 = NREG == 2 ? __fsqrt_rn(tk.v1) : 0.f;
             if (ES > 0) {   // park the list: ranks 0..ES-2 (>= K of them) and the row number in the last slot
-                if (lane < ES) epi[(int)(i - qb_p) * ES + lane] = lane == ES - 1 ? q.w : d0;
+                float* row = epi + (int)(i - qb_p) * ES;
+                if (ES <= 32) {
+                    if (lane < ES) row[lane] = lane == ES - 1 ? q.w : d0;
+                } else {   // ES == 33: all 32 ranks, the row number by lane 0
+                    row[lane] = d0;
+                    if (lane == 0) row[ES - 1] = q.w;
+                }
                 continue;
             }
             int valid = __popc(__ballot_sync(GSX_FULL, lane < K && d0 < 0.9e10f));

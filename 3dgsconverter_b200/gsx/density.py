@@ -87,6 +87,10 @@ def member_mask(xyz: torch.Tensor, voxel_size: float, keep_vox: np.ndarray, ws: 
     n = xyz.shape[0]
     keep_vox = np.ascontiguousarray(keep_vox, dtype=np.int64).reshape(-1, 3)
     need = max(64, 1 << int(np.ceil(np.log2(max(2 * len(keep_vox), 1))))) * 16 + 256   # two-word keys if far apart
+    if len(keep_vox):   # room for the bitmap form of the set (one bit per voxel of the kept voxels' box, <= 16 MiB)
+        bits = int(np.prod((keep_vox.max(axis=0) - keep_vox.min(axis=0) + 1).astype(np.float64)))
+        if bits <= (1 << 27):
+            need = max(need, bits // 8 + 256)
     if ws is None or ws.numel() < need:
         ws = torch.empty(need, dtype=torch.uint8, device=xyz.device)
     mask = torch.empty(n, dtype=torch.uint8, device=xyz.device)

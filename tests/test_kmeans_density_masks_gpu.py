@@ -105,6 +105,35 @@ def test_density_huge_extent_wide_keys(cuda, gsx_lib):
         assert np.array_equal(got.cpu().numpy(), want), (vs, thr, multi)
 
 
+def test_density_member_mask_bitmap_and_hash_sets(cuda, gsx_lib):
+    """The keep set is a bitmap over the kept voxels' bounding box when that box has <= 2^27 voxels and a hash set
+    otherwise (21-bit keys here; two-word keys in the test above): same mask, and both equal the oracle.  Two dense
+    blobs 900 voxels apart on every axis (box 900^3 > 2^27 -> hash set when both are kept, bitmap when one is)."""
+    import torch
+    import oracle
+    from gsx import density
+    rng = np.random.default_rng(11)
+    blob = rng.normal(0, 1.5, (40_000, 3))
+    xyz = np.r_[blob, rng.normal(0, 1.5, (25_000, 3)) + 900.0, rng.uniform(-20, 920, (5_000, 3))].astype(np.float32)
+    x = torch.from_numpy(xyz).to(cuda)
+    for multi in (True, False):
+        want, info_o = oracle.density_mask(xyz, voxel_size=1.0, threshold_percentage=0.05, keep_multicluster=multi)
+        got, info = density.density_filter(x, 1.0, 0.05, keep_multicluster=multi)
+        assert info["clusters"] == info_o["clusters"] and info["clusters"] >= 1
+        assert np.array_equal(got.cpu().numpy(), want), multi
+    # explicit keep lists straight into gsx_density_member_mask: a compact set (bitmap), the same set plus one far
+    # voxel (hash), with points on voxel borders and outside the box on every side
+    pts = np.r_[rng.uniform(-3, 12, (20_000, 3)), np.array([[5000.5, 5000.5, 5000.5], [-1e6, 3, 3], [3, 1e6, 3]])]
+    pts = np.r_[pts, np.floor(rng.uniform(-3, 12, (2_000, 3)))].astype(np.float32)
+    keep = np.unique(rng.integers(0, 9, (300, 3)), axis=0).astype(np.int64)
+    vox = np.floor(pts / np.float32(1.0)).astype(np.int64)
+    for extra in (np.zeros((0, 3), np.int64), np.array([[5000, 5000, 5000]], np.int64)):
+        k = np.r_[keep, extra]
+        want = (vox[:, None, :] == k[None, :, :]).all(-1).any(-1)
+        got = density.member_mask(torch.from_numpy(pts).to(cuda), 1.0, k)
+        assert np.array_equal(got.cpu().numpy().astype(bool), want), len(extra)
+
+
 def test_bbox_alpha_match_oracle(cuda, gsx_lib):
     import torch
     import oracle
