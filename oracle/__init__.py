@@ -10,8 +10,9 @@ cannot be installed here, so nothing below was ever compared with a Taichi RUN. 
     /root/reference/gsconverter/processing/gpu_ops.py executed unmodified under a serial stand-in for the
     `taichi` module (tests/golden/ti_serial.py, assumptions T1-T5 stated there: i32/f32 defaults, wrapping
     i32 products, strict IEEE per operation, serial atomics) -> tests/golden/g4_reference_kernels.npz
-    (11 SOR runs on 8 clouds <= 3000 points, 4 K-Means problems), tests/test_reference_kernels_pin.py.
-    Larger sizes rest on this restatement plus the survey's anchor counts: "parity unpinned" beyond 3000 points.
+    (11 SOR runs on 8 clouds <= 3000 points, 4 K-Means problems) and g5_reference_sor_100k.npz (BASELINE
+    configs[0]: the 100 k cloud, k=27 / --sor_intensity 5 and k=16), tests/test_reference_kernels_pin.py.
+    Larger sizes rest on this restatement plus the survey's anchor counts: "parity unpinned" beyond 100 k points.
   * density / alpha / bbox / cKDTree SOR arithmetic: to the imported reference (tests/golden/make_goldens.py);
   * NumPy-visible arithmetic (pairwise mean/std, promotion rules): to NumPy itself (tests/test_oracle_pins.py).
 """

@@ -103,6 +103,51 @@ def test_stand_in_executes_the_reference_source_live():
     assert np.array_equal(L, Lo) and np.array_equal(C.view(np.uint32), Co.view(np.uint32))
 
 
+# ---- BASELINE configs[0]: the 100 k cloud, --sor_intensity 5 (k=27) and k=16, through the reference's source
+G5 = GOLD.parent / "g5_reference_sor_100k.npz"
+
+
+def _sha(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def test_100k_cloud_reference_source_vs_oracle_and_older_fixture():
+    """g5 (make_taichi_golden_100k.py, ~20 min of the stand-in) holds digests of what the reference's filter_sor_gpu
+    source returns for the 100 k `mixed` cloud; the oracle reproduces them, the full k=16 vector stored in g1_100k.npz
+    (an ORACLE output, made before the stand-in existed) carries the same digest, and the removed count is the
+    survey's independent anchor (247)."""
+    import oracle
+    from gsx import synth
+    g5, g1 = np.load(G5), np.load(GOLD.parent / "g1_100k.npz")
+    xyz = synth.xyz(100_000, "mixed")
+    assert _sha(xyz) == str(g5["xyz_sha"])
+    assert int(g5["k16_removed"]) == 247 and int(g5["k27_removed"]) == 5
+    assert _sha(g1["tai_k16_means"]) == str(g5["k16_means_sha"])
+    assert str(g1["tai_k27_sha"]) == str(g5["k27_means_sha"])
+    for k in (16, 27):
+        md = oracle.sor_taichi_mean_dists(xyz, k, "i32wrap")
+        assert _sha(md) == str(g5[f"k{k}_means_sha"]), k
+        mask = oracle.threshold_mask(md, float(g5[f"k{k}_sigma"]))
+        assert _sha(np.packbits(mask)) == str(g5[f"k{k}_mask_sha"]), k
+
+
+@pytest.mark.gpu
+def test_cuda_100k_cloud_matches_reference_source_digests(cuda, gsx_lib):
+    import torch
+    from gsx import sor, synth
+    from gsconverter.processing import gpu_ops
+    g5 = np.load(G5)
+    xyz = synth.xyz(100_000, "mixed")
+    x = torch.from_numpy(xyz).to(cuda)
+    for k in (16, 27):
+        sigma = float(g5[f"k{k}_sigma"])
+        m, md = sor.sor_filter(x, k, sigma, hash_mode="i32wrap", return_means=True)
+        assert _sha(md.cpu().numpy()) == str(g5[f"k{k}_means_sha"]), k
+        assert _sha(np.packbits(m.cpu().numpy())) == str(g5[f"k{k}_mask_sha"]), k
+        assert _sha(np.packbits(gpu_ops.filter_sor_gpu(xyz, k=k, threshold_factor=sigma))) == str(g5[f"k{k}_mask_sha"])
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 def test_cuda_sor_matches_reference_kernel_outputs(cuda, gsx_lib):
