@@ -950,6 +950,10 @@ __device__ __forceinline__ float warp_sort32(float v, int lane) {
 #ifndef GSX_KNN_FIRST_SORT
 #define GSX_KNN_FIRST_SORT 1
 #endif
+// long buckets that span fewer than this many supers (1024 points each) skip the super-box level (0: never)
+#ifndef GSX_KNN_FLAT_SUPERS
+#define GSX_KNN_FLAT_SUPERS 0
+#endif
 // Epilogue of a query (gpu_ops.py:163-174: serial float32 sum of the valid distances, mean) -- batched: every query
 // of a batch parks its K ascending distances and its row number in shared memory, and after the batch lane q sums
 // query q (16 serial sums run side by side instead of one shuffle + add per rank on lane 0 of every query).
@@ -1230,6 +1234,34 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
                 const int skip = p == 13 ? skip_chunk : -1;
                 const int fc = s >> 5, lc = (int)((e - 1) >> 5);
                 const int fs = fc >> 5, ls = lc >> 5;
+                // the 32 chunks cbase .. cbase+31: box test per lane, then nearest box first while it can still improve
+                auto chunk_group = [&](const int cbase) {
+                    const int cid = cbase + lane;
+                    const bool cv = cid >= fc && cid <= lc && cid != skip;
+                    unsigned ckey = 0xffffffffu;
+                    if (cv) {
+                        float lb = box_lb(caabb, cid, q.x, q.y, q.z);
+                        if (lb < tk.tau) ckey = __float_as_uint(lb);
+                    }
+                    if (STATS) st_boxes += __popc(__ballot_sync(GSX_FULL, cv));
+                    for (;;) {
+                        unsigned mc = __reduce_min_sync(GSX_FULL, ckey);
+                        if (mc == 0xffffffffu || !(__uint_as_float(mc) < tk.tau)) break;
+                        int srcc = __ffs(__ballot_sync(GSX_FULL, ckey == mc)) - 1;
+                        if (lane == srcc) ckey = 0xffffffffu;
+                        const pos_t j = ((pos_t)(cbase + srcc) << 5) + lane;
+                        scan32<NREG, STATS>(spos, j, j >= s && j < e, q.x, q.y, q.z, tk, lane, st_scanned);
+                    }
+                };
+#if GSX_KNN_FLAT_SUPERS > 0
+                // a bucket of a few supers: every super box is near the query (it sits in or next to this bucket), so
+                // the super level prunes nothing -- test the chunk boxes directly, 32 at a time (exact either way: a
+                // chunk is skipped only when its lower bound is >= the current tau, and tau never grows)
+                if (ls - fs < GSX_KNN_FLAT_SUPERS) {
+                    for (int cb = fc; cb <= lc; cb += 32) chunk_group(cb);
+                    continue;
+                }
+#endif
                 for (int sb = fs; sb <= ls; sb += 32) {
                     const int sid = sb + lane;
                     unsigned skey = 0xffffffffu;
@@ -1243,23 +1275,7 @@ __global__ void __launch_bounds__(256, GSX_KNN_MINBLOCKS)
                         if (ms == 0xffffffffu || !(__uint_as_float(ms) < tk.tau)) break;
                         int srcs = __ffs(__ballot_sync(GSX_FULL, skey == ms)) - 1;
                         if (lane == srcs) skey = 0xffffffffu;
-                        const int sup = sb + srcs;
-                        const int cid = sup * 32 + lane;
-                        const bool cv = cid >= fc && cid <= lc && cid != skip;
-                        unsigned ckey = 0xffffffffu;
-                        if (cv) {
-                            float lb = box_lb(caabb, cid, q.x, q.y, q.z);
-                            if (lb < tk.tau) ckey = __float_as_uint(lb);
-                        }
-                        if (STATS) st_boxes += __popc(__ballot_sync(GSX_FULL, cv));
-                        for (;;) {
-                            unsigned mc = __reduce_min_sync(GSX_FULL, ckey);
-                            if (mc == 0xffffffffu || !(__uint_as_float(mc) < tk.tau)) break;
-                            int srcc = __ffs(__ballot_sync(GSX_FULL, ckey == mc)) - 1;
-                            if (lane == srcc) ckey = 0xffffffffu;
-                            const pos_t j = ((pos_t)(sup * 32 + srcc) << 5) + lane;
-                            scan32<NREG, STATS>(spos, j, j >= s && j < e, q.x, q.y, q.z, tk, lane, st_scanned);
-                        }
+                        chunk_group((sb + srcs) * 32);
                     }
                 }
             }
@@ -1360,12 +1376,17 @@ static int launch_knn16(SorWs& w, int64_t q_begin, int64_t q_end, int q_stride, 
 // and checked by bench.py before it uses a capture's instruction count for the roofline
 #define GSX_STR2(x) #x
 #define GSX_STR(x) GSX_STR2(x)
+#if GSX_KNN_FLAT_SUPERS > 0
+#define GSX_FLAT_INFO ";flat_supers=" GSX_STR(GSX_KNN_FLAT_SUPERS)
+#else
+#define GSX_FLAT_INFO ""
+#endif
 const char* sor_build_info() {
     return "knn=r02c"
            ";epi_smem=" GSX_STR(GSX_KNN_EPI_SMEM) ";first_sort=" GSX_STR(GSX_KNN_FIRST_SORT)
            ";query_batch=" GSX_STR(GSX_QUERY_BATCH) ";minblocks=" GSX_STR(GSX_KNN_MINBLOCKS)
            ";merge_threshold=" GSX_STR(GSX_MERGE_THRESHOLD) ";small_bucket=" GSX_STR(GSX_SMALL_BUCKET)
-           ";knn16=" GSX_STR(GSX_KNN16) ";tma=" GSX_STR(GSX_KNN_TMA) ";i32=" GSX_STR(GSX_KNN_I32);
+           GSX_FLAT_INFO ";knn16=" GSX_STR(GSX_KNN16) ";tma=" GSX_STR(GSX_KNN_TMA) ";i32=" GSX_STR(GSX_KNN_I32);
 }
 
 int sor_mean_dists(SorWs& w, int64_t q_begin, int64_t q_end, int q_stride, int q_phase, int k, int hash_mode,

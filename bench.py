@@ -86,18 +86,23 @@ def c2_config(args, world):
 
 # ----------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  nvidia-smi needs ~0.1 s to produce its
+    first row and the default timed region is shorter than that, so the sampler is started BEFORE the warm-up steps
+    (25 ms period), every row is stamped with the host clock, and `stop()` keeps the rows that fall inside
+    [window_begin(), window_end()] -- the timed steps.  If the timed region was too short to catch a row, the rows
+    of the warm-up steps (the same kernels on the same data) are reported instead and `window` says so."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
         self.rows, self.proc, self.idx = [], None, gpu_index
+        self.t0 = self.t1 = self.extra_from = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                          "-lms", "25", "-i", str(self.idx)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -106,29 +111,82 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def window_begin(self):
+        self.t0 = time.monotonic()
+
+    def window_end(self):
+        self.t1 = time.monotonic()
+
+    def need_more(self) -> bool:
+        """True while no row fell into the timed window AND no row has arrived yet from the extra busy steps the caller
+        runs in the meantime (so the reported clocks are clocks UNDER LOAD, never idle clocks).  Gives up after 3 s."""
+        if not self.proc:
+            return False
+        if self.t0 is not None and self.t1 is None:
+            self.window_end()
+        if [1 for t, _ in self.rows if self.t0 is not None and self.t0 <= t <= self.t1]:
+            return False
+        if self.extra_from is None:
+            self.extra_from = time.monotonic()
+        if time.monotonic() > self.extra_from + 3.0:
+            return False
+        return not [1 for t, _ in self.rows if t > self.extra_from + 0.03]
+
+    def stop(self, keep_busy=None):
+        """keep_busy: callable that runs one more (untimed) step while need_more()."""
         if not self.proc:
             return None
+        while self.need_more():
+            if keep_busy is not None:
+                keep_busy()
+            else:
+                time.sleep(0.02)
+        self.t_stop = time.monotonic()
         self.proc.terminate()
         try:
             self.proc.wait(2)
         except Exception:
             self.proc.kill()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        if not sm:
+        ok = [(t, r) for t, r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        if not ok:
             return None
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        window = "timed region"
+        sel = [r for t, r in ok if self.t0 is not None and self.t0 <= t <= self.t1]
+        if not sel and self.extra_from is not None:
+            sel = [r for t, r in ok if self.extra_from + 0.03 < t <= self.t_stop]
+            window = "extra untimed steps right after the timed region (it was shorter than nvidia-smi's sampling period)"
+        if not sel:
+            sel = [r for _, r in ok]
+            window = "whole run (no row inside the timed region)"
+        sm = [float(r[1]) for r in sel]
+        mx = [float(r[2]) for r in sel if r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
-            if len(r) < 9:
-                continue
+        for r in sel:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
+
+
+def finish_clocks(clocks, world, rank, dev, busy_step):
+    """Stop the sampler on rank 0; while it still needs a row under load, EVERY rank runs extra untimed steps
+    (the step may contain collectives, so the decision is broadcast from rank 0)."""
+    import torch
+    sync = torch.cuda.synchronize if torch.device(dev).type == "cuda" else (lambda: None)
+    if world == 1:
+        return clocks.stop(keep_busy=lambda: (busy_step(), sync()))
+    import torch.distributed as dist
+    for _ in range(64):
+        need = torch.tensor([1 if (rank == 0 and clocks.need_more()) else 0], dtype=torch.int32, device=dev)
+        dist.broadcast(need, 0)
+        if int(need.item()) == 0:
+            break
+        busy_step()
+        sync()
+    return clocks.stop() if rank == 0 else None
 
 
 def peaks():
@@ -356,22 +414,24 @@ def run_c2(args):
         return gd.sor_filter_auto(xyz, K_SOR, SIGMA, args.hash)
 
     step.events = []
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()          # before the warm-up: nvidia-smi's first row takes longer than a short timed region
     for _ in range(args.warmup):
         mask = step(False)
     barrier(world)
     launches0 = _abi.lib.gsx_kernel_launches()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     t_start, t_end = ev(), ev()
     barrier(world)
+    clocks.window_begin()
     t_start.record()
     for _ in range(args.steps):
         mask = step(True)
     t_end.record()
     barrier(world)
-    clk = clocks.stop() if rank == 0 else None
+    clocks.window_end()
     launches = _abi.lib.gsx_kernel_launches() - launches0
+    clk = finish_clocks(clocks, world, rank, dev, lambda: step(False))
     elapsed_ms = max_over_ranks(t_start.elapsed_time(t_end), dev, world)
     ms_per_step = elapsed_ms / args.steps
     value = n_total / (ms_per_step * 1e-3) / 1e6
@@ -871,22 +931,23 @@ def run_big(args):
         torch.cuda.synchronize()
         return a.elapsed_time(b), nch, rows, sha(C), X, init
 
-    for _ in range(max(1, min(args.warmup, 2))):
-        chain_once(xyz, op, world > 1)
-    barrier(world)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    for _ in range(max(1, min(args.warmup, 2))):
+        chain_once(xyz, op, world > 1)
+    barrier(world)
     l0 = _abi.lib.gsx_kernel_launches()
     steps = max(1, args.steps)
     t0e, t1e = ev(), ev()
     barrier(world)
+    clocks.window_begin()
     t0e.record()
     for _ in range(steps):
         ch, counts, marks = chain_once(xyz, op, world > 1)
     t1e.record()
     barrier(world)
-    launches = _abi.lib.gsx_kernel_launches() - l0
+    launches = _abi.lib.gsx_kernel_launches() - l0      # (the clock window stays open over the K-Means part below)
     ms_chain = max_over_ranks(t0e.elapsed_time(t1e), dev, world) / steps
     stage = {}
     names = (["bbox+alpha", "density", "sor"] if full_chain else ["density", "sor"])
