@@ -290,6 +290,9 @@ int gsx_sor_filter_host(const float* xyz_host, int64_t n, int32_t k, float thres
     if ((rc = gsx_sor_filter_device((const float*)xyz.p, n, k, threshold_factor, hash_mode, (uint8_t*)mask.p,
                                     (float*)means.p, ws.p, wsb, st)))
         return rc;
+    // the kernels are queued: make the (usually never touched) destination pages resident while the GPU works
+    prefault_host(mask_host, (size_t)n);
+    if (means_host) prefault_host(means_host, (size_t)n * 4);
     if ((rc = copy_d2h(mask_host, mask.p, (size_t)n, st))) return rc;
     if (means_host && (rc = copy_d2h(means_host, means.p, (size_t)n * 4, st))) return rc;
     GSX_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -352,6 +355,9 @@ int gsx_sor_ckdtree_filter_host(const float* xyz_host, int64_t n, int32_t k, flo
     if ((rc = mean_std_f32((const float*)means.p, n, (float*)ms.p, msws.p, (size_t)msb, st))) return rc;
     if ((rc = threshold_mask((const float*)means.p, n, (const float*)ms.p, threshold_factor, (uint8_t*)mask.p, st)))
         return rc;
+    // the kernels are queued: make the (usually never touched) destination pages resident while the GPU works
+    prefault_host(mask_host, (size_t)n);
+    if (means_host) prefault_host(means_host, (size_t)n * 4);
     if ((rc = copy_d2h(mask_host, mask.p, (size_t)n, st))) return rc;
     if (means_host && (rc = copy_d2h(means_host, means.p, (size_t)n * 4, st))) return rc;
     GSX_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -474,6 +480,7 @@ int gsx_kmeans_host(const float* X_host, int64_t n, int32_t K, int32_t D, int32_
     int64_t off[2] = {0, n};
     if ((rc = kmeans_lloyd((const float*)X.p, off, 1, K, D, max_iter, (float*)C.p, (int*)L.p, (int*)cnt.p, ws.p, wsb, assign_mode, nullptr, st)))
         return rc;
+    prefault_host(labels_host, (size_t)n * 4);   // while the Lloyd iterations run
     GSX_CUDA_CHECK(cudaMemcpyAsync(C_host_inout, C.p, (size_t)K * D * 4, cudaMemcpyDeviceToHost, st));
     if ((rc = copy_d2h(labels_host, L.p, (size_t)n * 4, st))) return rc;
     GSX_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -503,6 +510,7 @@ int gsx_kmeans_host_batched(const float* X_host, const int64_t* row_off_host, in
     if ((rc = kmeans_lloyd((const float*)X.p, row_off_host, nprob, K, D, max_iter, (float*)C.p, (int*)L.p, (int*)cnt.p,
                            ws.p, wsb, assign_mode, nullptr, st)))
         return rc;
+    prefault_host(labels_host, (size_t)n * 4);   // while the Lloyd iterations run
     GSX_CUDA_CHECK(cudaMemcpyAsync(C_host_inout, C.p, (size_t)nprob * K * D * 4, cudaMemcpyDeviceToHost, st));
     if ((rc = copy_d2h(labels_host, L.p, (size_t)n * 4, st))) return rc;
     GSX_CUDA_CHECK(cudaStreamSynchronize(st));

@@ -23,6 +23,15 @@ for mb in (120, 1100):
         for _ in range(5):
             torch.cuda.synchronize(); t0 = time.perf_counter(); b = down(); ts.append(time.perf_counter() - t0)
         res[f"d2h_{mb}MB_{name}_GBps"] = round(mb / 1e3 / min(ts[1:]), 1)
+    from gsx._abi import lib
+    dst = np.zeros(a.nbytes, dtype=np.uint8)      # touched destination (what prefault_host buys the *_host entries)
+    ts = []
+    for _ in range(5):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        lib.gsx_copy_d2h(dst.ctypes.data, t.data_ptr(), dst.nbytes, None); ts.append(time.perf_counter() - t0)
+    res[f"d2h_{mb}MB_staged_touched_dst_GBps"] = round(mb / 1e3 / min(ts[1:]), 1)
+    assert np.array_equal(dst, a)
+    del dst
     p = torch.from_numpy(a).pin_memory()
     ts = []
     for _ in range(5):
@@ -32,9 +41,10 @@ for mb in (120, 1100):
 print(json.dumps(res))
 '''
 out = {}
-for T in (2, 4, 8, 12, 16):
-    r = subprocess.run([sys.executable, "-c", CHILD], env=dict(os.environ, GSX_COPY_THREADS=str(T)), capture_output=True,
-                       text=True, timeout=300)
-    out[f"threads={T}"] = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": r.stderr[-300:]}
-    print(T, json.dumps(out[f"threads={T}"]), flush=True)
+for T, chunk_kb in ((8, 1024), (8, 4096), (4, 1024), (16, 1024), (8, 256)):
+    r = subprocess.run([sys.executable, "-c", CHILD], env=dict(os.environ, GSX_COPY_THREADS=str(T), GSX_COPY_CHUNK_KB=str(chunk_kb)),
+                       capture_output=True, text=True, timeout=300)
+    key = f"threads={T},chunk_kb={chunk_kb}"
+    out[key] = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": r.stderr[-300:]}
+    print(key, json.dumps(out[key]), flush=True)
 json.dump(out, open("gpurun_out/copy_threads_probe.json", "w"), indent=1)
