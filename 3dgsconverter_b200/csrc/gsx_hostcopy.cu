@@ -30,8 +30,9 @@ namespace {
 
 constexpr size_t kStagedMin = 8u << 20;      // below this the plain path is as fast
 constexpr int kMaxThreads = 16;
-size_t kChunk = 1u << 20;                    // pinned chunk (GSX_COPY_CHUNK_KB, default 1 MiB: the first DMA starts after
-                                             // ~80 us of memcpy; 4 MiB chunks measured 28 GB/s on a 120 MB upload)
+size_t kChunk = 4u << 20;                    // pinned chunk (GSX_COPY_CHUNK_KB, default 4 MiB; A/B in
+                                             // profiles/r02c_copy_threads_probe.json: 1 MiB chunks lose 25 % on a 1.1 GB
+                                             // upload, 256 KiB chunks lose half)
 
 // The helper threads are created once and parked on a condition variable: creating 7 threads and giving each a CUDA
 // context binding cost more than the copy itself for a 120 MB cloud.  Leaked on purpose (no static destruction order
@@ -123,7 +124,7 @@ bool pool_ready(Pool& p, int dev) {
         unsigned hw = std::thread::hardware_concurrency();
         int T = env_int("GSX_COPY_THREADS", hw >= 16 ? 8 : (hw >= 4 ? (int)hw / 2 : 1));
         p.T = std::max(1, std::min(T, kMaxThreads));
-        kChunk = (size_t)std::max(64, std::min(env_int("GSX_COPY_CHUNK_KB", 1024), 16384)) << 10;
+        kChunk = (size_t)std::max(64, std::min(env_int("GSX_COPY_CHUNK_KB", 4096), 16384)) << 10;
         if (cudaHostAlloc((void**)&p.pinned, 2 * (size_t)p.T * kChunk, cudaHostAllocPortable) != cudaSuccess) {
             cudaGetLastError();
             p.pinned = nullptr;

@@ -950,9 +950,10 @@ __device__ __forceinline__ float warp_sort32(float v, int lane) {
 #ifndef GSX_KNN_FIRST_SORT
 #define GSX_KNN_FIRST_SORT 1
 #endif
-// long buckets that span fewer than this many supers (1024 points each) skip the super-box level (0: never)
+// long buckets that span fewer than this many supers (1024 points each) skip the super-box level (0: never).
+// A/B (profiles/r02c_knn_variants.log): 8 -> -1.4 % on the mixed cloud (within ~1 % run-to-run noise), 32 -> +6 %.
 #ifndef GSX_KNN_FLAT_SUPERS
-#define GSX_KNN_FLAT_SUPERS 0
+#define GSX_KNN_FLAT_SUPERS 8
 #endif
 // Epilogue of a query (gpu_ops.py:163-174: serial float32 sum of the valid distances, mean) -- batched: every query
 // of a batch parks its K ascending distances and its row number in shared memory, and after the batch lane q sums
