@@ -688,6 +688,8 @@ def measure_like_for_like(xyz, xyz_np, args, cpu_bl):
                "ratio_e2e": round(ns / dt / 1e6 / cpu_bl["value"], 1),
                "kept": int(m.sum().item()), "kept_host_call": int(mh.sum())}
         # the full cloud on the GPU as well (the CPU side of that size is the --impl reference arm)
+        sor.ckdtree_filter(xyz, K_SOR, SIGMA)          # warm-up at this size (the first call grows torch's allocator)
+        torch.cuda.synchronize()
         a.record()
         mf = sor.ckdtree_filter(xyz, K_SOR, SIGMA)
         b.record()

@@ -147,3 +147,50 @@ def test_build_ops_glue_reaches_the_library(gsx_lib, monkeypatch):
     assert spos.shape == (1000, 4) and spos.data_ptr() >= ws.data_ptr()
     with pytest.raises(GsxError):
         ops.finish(ws, spos, 1000, bmin, cell)
+
+
+def _load_bench():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_bench_mod", ROOT / "bench.py")
+    mod = importlib.util.module_from_spec(spec)
+    old = sys.argv
+    sys.argv = ["bench.py"]
+    try:
+        spec.loader.exec_module(mod)
+    finally:
+        sys.argv = old
+    return mod
+
+
+def test_bench_clock_sampler_reports_clocks_under_load(tmp_path, monkeypatch):
+    """The bench contract needs `clocks` sampled DURING the timed region.  With a fake nvidia-smi whose first row takes
+    150 ms: (a) rows inside the window are used; (b) a timed region shorter than the sampler's start-up makes the caller
+    run extra busy steps until a row arrives -- never an idle-clock row from after the run."""
+    import os
+    import time
+    fake = tmp_path / "nvidia-smi"
+    fake.write_text("#!/bin/bash\nsleep 0.15\nwhile true; do echo '0, 1965, 1965, 400.0, 0x0, Not Active, Not Active, "
+                    "Not Active, Active'; sleep 0.025; done\n")
+    fake.chmod(0o755)
+    monkeypatch.setenv("PATH", f"{tmp_path}:{os.environ['PATH']}")
+    bench = _load_bench()
+    c = bench.ClockSampler(0)
+    c.start()
+    time.sleep(0.3)
+    c.window_begin()
+    time.sleep(0.1)
+    c.window_end()
+    r = c.stop()
+    assert r["window"] == "timed region" and r["samples"] >= 2 and r["sm_mhz"] == 1965.0
+    assert r["reasons"] == ["sw_power_cap"]
+    c = bench.ClockSampler(0)
+    c.start()
+    c.window_begin()
+    time.sleep(0.03)
+    c.window_end()
+    busy = []
+    r = c.stop(keep_busy=lambda: (busy.append(1), time.sleep(0.01)))
+    assert r is not None and len(busy) >= 5 and r["window"].startswith("extra untimed steps")
+    import torch
+    r = bench.finish_clocks(bench.ClockSampler(0), 1, 0, torch.device("cpu"), lambda: None)   # never started: no clocks
+    assert r is None
