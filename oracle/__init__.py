@@ -11,7 +11,8 @@ cannot be installed here, so nothing below was ever compared with a Taichi RUN. 
     `taichi` module (tests/golden/ti_serial.py, assumptions T1-T5 stated there: i32/f32 defaults, wrapping
     i32 products, strict IEEE per operation, serial atomics) -> tests/golden/g4_reference_kernels.npz
     (11 SOR runs on 8 clouds <= 3000 points, 4 K-Means problems) and g5_reference_sor_100k.npz (BASELINE
-    configs[0]: the 100 k cloud, k=27 / --sor_intensity 5 and k=16), tests/test_reference_kernels_pin.py.
+    configs[0]: the 100 k cloud, k=27 / --sor_intensity 5 and k=16) and g6_reference_kmeans_c3shape.npz (one
+    20 011 x 45, K=256 Lloyd problem -- the C3 / tensor-core shape), tests/test_reference_kernels_pin.py.
     Larger sizes rest on this restatement plus the survey's anchor counts: "parity unpinned" beyond 100 k points.
   * density / alpha / bbox / cKDTree SOR arithmetic: to the imported reference (tests/golden/make_goldens.py);
   * NumPy-visible arithmetic (pairwise mean/std, promotion rules): to NumPy itself (tests/test_oracle_pins.py).

@@ -27,7 +27,18 @@ def _sor_cases(g):
             yield name, int(kpart[1:]), float(spart[1:]), g[f"sor_{name}_xyz"], g[key], g[stem + "_mask"]
 
 
+G6 = GOLD.parent / "g6_reference_kmeans_c3shape.npz"   # one problem of the C3 shape (D=45, K=256), same key layout
+
+
+def _km_files():
+    return [np.load(GOLD)] + ([np.load(G6)] if G6.exists() else [])
+
+
 def _km_cases(g):
+    if isinstance(g, list):
+        for f in g:
+            yield from _km_cases(f)
+        return
     for key in g.files:
         if key.startswith("km_") and key.endswith("_meta"):
             name = key[3:-5]
@@ -40,8 +51,9 @@ def test_fixture_covers_the_reference_branches():
     g = np.load(GOLD)
     sor = {(n, k) for n, k, *_ in _sor_cases(g)}
     assert len(sor) == 11 and ("mixed3k", 80) in sor and ("identical64", 16) in sor and ("tiny5", 16) in sor
-    km = {c[0]: c for c in _km_cases(g)}
-    assert set(km) == {"sh45", "dups3", "codebook1d", "lattice"}
+    km = {c[0]: c for c in _km_cases(_km_files())}
+    assert set(km) == {"sh45", "dups3", "codebook1d", "lattice", "c3shape"}
+    assert km["c3shape"][1].shape == (20_011, 45) and km["c3shape"][2] == 256      # the tensor-core assign's shape
     # the duplicate-init case really leaves a cluster empty -> centroid row of zeros (gpu_ops.py:78-96)
     name, X, K, iters, seed, rows, C, L = km["dups3"]
     assert len(np.unique(X[rows], axis=0)) < K
@@ -68,8 +80,7 @@ def test_oracle_reproduces_reference_sor_kernel():
 
 def test_oracle_reproduces_reference_kmeans_kernels():
     import oracle
-    g = np.load(GOLD)
-    for name, X, K, iters, seed, rows, C, L in _km_cases(g):
+    for name, X, K, iters, seed, rows, C, L in _km_cases(_km_files()):
         np.random.seed(seed)
         assert np.array_equal(np.random.choice(len(X), K, replace=False), rows)   # the reference's draw (gpu_ops.py:182)
         Co, Lo, cnt = oracle.kmeans_lloyd(X, K, iters, init=X[rows])
@@ -175,8 +186,7 @@ def test_plugin_filter_sor_gpu_matches_reference_outputs(cuda, gsx_lib):
 def test_cuda_kmeans_matches_reference_kernel_outputs(assign, cuda, gsx_lib):
     import torch
     from gsx import kmeans as gk
-    g = np.load(GOLD)
-    for name, X, K, iters, seed, rows, C, L in _km_cases(g):
+    for name, X, K, iters, seed, rows, C, L in _km_cases(_km_files()):
         Cg, Lg, cnt = gk.kmeans_lloyd(torch.from_numpy(X).to(cuda), K, iters, init=torch.from_numpy(X[rows]).to(cuda),
                                       assign=assign)
         assert np.array_equal(Lg.cpu().numpy(), L), (name, assign)
@@ -187,8 +197,7 @@ def test_cuda_kmeans_matches_reference_kernel_outputs(assign, cuda, gsx_lib):
 def test_plugin_kmeans_matches_reference_outputs(cuda, gsx_lib):
     """gpu_ops.kmeans(numpy) with the global NumPy RNG seeded as in the generator: same draw, same result."""
     from gsconverter.processing import gpu_ops
-    g = np.load(GOLD)
-    for name, X, K, iters, seed, rows, C, L in _km_cases(g):
+    for name, X, K, iters, seed, rows, C, L in _km_cases(_km_files()):
         np.random.seed(seed)
         Cg, Lg = gpu_ops.kmeans(X.copy(), K, max_iter=iters)
         assert Lg.dtype == np.int32 and np.array_equal(Lg, L), name
