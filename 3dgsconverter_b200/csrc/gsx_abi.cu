@@ -8,6 +8,7 @@
 #include "gsx_compact.cuh"
 #include "gsx_density.cuh"
 #include "gsx_hostcopy.cuh"
+#include "gsx_hostrows.cuh"
 #include "gsx_kmeans.cuh"
 #include "gsx_knn_exact.cuh"
 #include "gsx_masks.cuh"
@@ -525,6 +526,17 @@ int gsx_copy_h2d(void* dst_dev, const void* src_host, int64_t bytes, void* strea
 int gsx_copy_d2h(void* dst_host, const void* src_dev, int64_t bytes, void* stream) {
     GSX_REQUIRE(bytes >= 0 && (bytes == 0 || (dst_host && src_dev)), GSX_ERR_ARG, "copy_d2h: bad arguments");
     return copy_d2h(dst_host, src_dev, (size_t)bytes, (cudaStream_t)stream);
+}
+
+/* ------------------------------------------------------------------ host-resident records: threaded row movement */
+int gsx_host_gather_rows(const void* src_host, int64_t n_rows, int64_t row_bytes, const int64_t* idx_host, int64_t m,
+                         void* dst_host) {
+    return host_gather_rows(src_host, n_rows, row_bytes, idx_host, m, dst_host);
+}
+int gsx_host_extract_xyz_opacity(const void* src_host, int64_t n_rows, int64_t row_bytes, int64_t off_x, int64_t off_y,
+                                 int64_t off_z, int64_t off_opacity, float* xyz_out_host, float* opacity_out_host) {
+    return host_extract_xyz_opacity(src_host, n_rows, row_bytes, off_x, off_y, off_z, off_opacity, xyz_out_host,
+                                    opacity_out_host);
 }
 
 /* ------------------------------------------------------------------ device-resident records (SURVEY 8f 2,4) */

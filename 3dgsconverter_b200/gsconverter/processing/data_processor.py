@@ -58,7 +58,8 @@ class DataProcessor:
                     self._records = self._records.gather(self._chain.idx)
                 self._data = self._records.to_host()
             else:
-                self._data = self._data[self._chain.indices()]
+                from gsx import hostrows
+                self._data = hostrows.take_rows(self._data, self._chain.indices())   # vertices[mask], threaded
             self._chain.rebase()
             self._pending = False
         return self._data
@@ -88,8 +89,8 @@ class DataProcessor:
                     xyz, op = self._records.xyz_opacity()
                     self._chain = FilterChain(xyz, op)
                     return self._chain
-            xyz = np.column_stack((v["x"], v["y"], v["z"]))
-            op = v["opacity"] if "opacity" in v.dtype.names else None
+            from gsx import hostrows
+            xyz, op = hostrows.xyz_opacity(v)        # np.column_stack((x, y, z)), v["opacity"] -- threaded
             self._chain = FilterChain(xyz, op)
         return self._chain
 

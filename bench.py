@@ -542,6 +542,10 @@ def run_c2(args):
         line["like_for_like"] = measure_like_for_like(xyz, xyz_np, args, line["cpu_baseline"])
         line["other_modes"] = measure_other(xyz, ws, means, args)
         line["pipeline"] = measure_pipeline(xyz_np, args)
+        try:
+            line["host_rows"] = measure_host_rows(xyz_np)
+        except Exception as e:  # noqa: BLE001  (an extra: never lose the bench line over it)
+            line["host_rows"] = {"error": str(e)[:200]}
         del ws
         torch.cuda.empty_cache()
         line["kmeans"] = measure_kmeans(dev, full=True)
@@ -762,6 +766,40 @@ def measure_pipeline(xyz_np, args):
     return {"what": "bbox -> alpha(5) -> density(0.5, multicluster) -> SOR k=16, host columns in, surviving indices out",
             "ms": round(dt * 1e3, 2), "msplats_s": round(n / dt / 1e6, 2), "survivors_per_stage": list(counts[:4]),
             "h2d_bytes": int(n * 16), "d2h_bytes": int(counts[4] * 4)}
+
+
+def measure_host_rows(xyz_np, n=1_000_000):
+    """Host-resident records (a1: where the reference's time goes once the masks are cheap): np.column_stack of the
+    filter columns and the `vertices[mask]` gather of 248-byte records, NumPy (one thread) vs libgsx's threaded
+    gsx_host_extract_xyz_opacity / gsx_host_gather_rows, on a 1 M-record sample with 60 % survivors (NumPy's structured
+    fancy index takes seconds per million records, so the sample is kept small).  CPU only."""
+    from gsx import hostrows
+    n = min(n, len(xyz_np))
+    names = (["x", "y", "z", "nx", "ny", "nz", "f_dc_0", "f_dc_1", "f_dc_2"] + [f"f_rest_{i}" for i in range(45)] +
+             ["opacity", "scale_0", "scale_1", "scale_2", "rot_0", "rot_1", "rot_2", "rot_3"])   # structures.py:23-59
+    rec = np.zeros(n, dtype=[(nm, "f4") for nm in names])
+    rec["x"], rec["y"], rec["z"] = xyz_np[:n, 0], xyz_np[:n, 1], xyz_np[:n, 2]
+    idx = np.flatnonzero(np.random.default_rng(3).random(n) < 0.6).astype(np.int64)
+
+    def best(fn, reps=3):
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            r = fn()
+            ts.append(time.perf_counter() - t0)
+        return min(ts), r
+    t_np, a = best(lambda: rec[idx], reps=1)
+    t_gx, b = best(lambda: hostrows.take_rows(rec, idx))
+    same = a.tobytes() == b.tobytes()
+    del a, b
+    t_np2, c = best(lambda: np.column_stack((rec["x"], rec["y"], rec["z"])), reps=2)
+    t_gx2, d = best(lambda: hostrows.xyz_opacity(rec))
+    same = same and c.tobytes() == d[0].tobytes()
+    return {"records": n, "record_bytes": rec.dtype.itemsize, "survivors": int(len(idx)), "identical_bytes": bool(same),
+            "gather_rows": {"numpy_ms": round(t_np * 1e3, 1), "gsx_ms": round(t_gx * 1e3, 1),
+                            "gsx_GBps_read_plus_write": round(len(idx) * rec.dtype.itemsize * 2 / t_gx / 1e9, 1)},
+            "column_stack_xyz": {"numpy_ms": round(t_np2 * 1e3, 1), "gsx_ms": round(t_gx2 * 1e3, 1)},
+            "threads": os.environ.get("GSX_HOST_THREADS", "default (16 on a host with >= 32 cores)")}
 
 
 # ----------------------------------------------------------------------------- c3: K-Means (secondary BASELINE metric)

@@ -310,6 +310,17 @@ int gsx_kmeans_host_batched(const float* X_host, const int64_t* row_off_host, in
  * gsx_copy_d2h: waits for what `stream` has produced and BLOCKS until dst_host is complete. */
 int gsx_copy_h2d(void* dst_dev, const void* src_host, int64_t bytes, void* stream);
 int gsx_copy_d2h(void* dst_host, const void* src_dev, int64_t bytes, void* stream);
+/* HOST-side row movement around the device filter chain when the 248-byte records stay on the host (no GPU work, several
+ * CPU threads -- GSX_HOST_THREADS, default 16 on a big host): what the reference does with single-threaded NumPy.
+ * gsx_host_gather_rows: dst[j] = src[idx[j]] for rows of row_bytes bytes -- the `vertices[mask]` compaction of
+ *   data_processor.py:114,149,209,224 with the surviving row indices; every idx must lie in [0, n_rows).
+ * gsx_host_extract_xyz_opacity: np.column_stack((v['x'], v['y'], v['z'])) and v['opacity'] of data_processor.py:38,139
+ *   from packed records; the fields are float32 at the given byte offsets of a row (off_opacity < 0 and a null
+ *   opacity_out_host: no opacity field). */
+int gsx_host_gather_rows(const void* src_host, int64_t n_rows, int64_t row_bytes, const int64_t* idx_host, int64_t m,
+                         void* dst_host);
+int gsx_host_extract_xyz_opacity(const void* src_host, int64_t n_rows, int64_t row_bytes, int64_t off_x, int64_t off_y,
+                                 int64_t off_z, int64_t off_opacity, float* xyz_out_host, float* opacity_out_host);
 /* Free / total memory of the current device, for the sizing decisions of the host-buffer callers. */
 int gsx_device_memory(int64_t* free_bytes, int64_t* total_bytes);
 
