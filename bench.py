@@ -649,7 +649,18 @@ def measure_cpu_baseline(xyz_np, args):
     cores = os.cpu_count() or 1
     dt, kept = cpu_reference_sor(sample, K_SOR, SIGMA)
     dt2, kept2 = cpu_taichi_port_sor(sample, K_SOR, SIGMA, args.hash)
-    return {"value": round(ns / dt / 1e6, 4), "unit": "Msplats/s", "cores": cores, "kind": "port",
+    dens = None
+    try:   # SURVEY 8(d) CPU baseline (b): the reference's NumPy density filter (data_processor.py:11-117), same sample
+        import oracle
+        t0 = time.perf_counter()
+        dmask, dinfo = oracle.density_mask(sample, sensitivity=0.5, keep_multicluster=True)
+        dt3 = time.perf_counter() - t0
+        dens = {"value": round(ns / dt3 / 1e6, 4), "unit": "Msplats/s", "seconds": round(dt3, 3), "kept": int(dmask.sum()),
+                "what": "apply_density_filter(sensitivity=0.5, keep_multicluster) as NumPy (oracle/filters.py, pinned to the "
+                        "imported reference by tests/golden/make_goldens.py), one thread, same sample"}
+    except Exception as e:  # noqa: BLE001
+        dens = {"error": str(e)[:200]}
+    return {"density": dens, "value": round(ns / dt / 1e6, 4), "unit": "Msplats/s", "cores": cores, "kind": "port",
             "sample": f"first {ns} points of the bench cloud, one pass; reference CPU path = SciPy cKDTree "
                       f"(k+1)-NN on cpu_count()-1={max(1, cores - 1)} workers + mean/std mask "
                       f"(data_processor.py:155-180); the --impl reference arm times the full cloud",
@@ -723,6 +734,22 @@ def measure_other(xyz, ws, means, args):
         torch.cuda.synchronize()
         return a.elapsed_time(b) / 5
 
+    try:   # the density filter alone on the resident cloud (BASELINE configs[1]: density_sensitivity 0.5)
+        from gsx import density
+        for _ in range(2):
+            density.density_filter(xyz, sensitivity=0.5, keep_multicluster=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            dm, dinfo = density.density_filter(xyz, sensitivity=0.5, keep_multicluster=True)
+        torch.cuda.synchronize()
+        dms = (time.perf_counter() - t0) / 3 * 1e3
+        out[f"density_0.5_multicluster_{args.kind}"] = {"ms": round(dms, 3), "msplats_s": round(xyz.shape[0] / dms / 1e3, 2),
+                                                       "kept": int(dm.sum().item()), "clusters": int(dinfo["clusters"]),
+                                                       "note": "wall clock incl. the host cluster selection between the "
+                                                               "two device stages"}
+    except Exception as e:  # noqa: BLE001
+        out["density_error"] = str(e)[:200]
     other = "i64" if args.hash == "i32wrap" else "i32wrap"
     ms = timed(xyz, other)
     out[f"{args.kind}_{other}"] = {"ms": round(ms, 3), "msplats_s": round(xyz.shape[0] / ms / 1e3, 2)}
