@@ -1,4 +1,5 @@
-// host-only harness: gsx_hostcopy.cu against the mock runtime, many sizes, several caller threads, under -fsanitize=thread
+// host-only harness: gsx_hostcopy.cu against the mock runtime (asynchronous streams, see cuda_runtime.h), many sizes,
+// several caller threads, under -fsanitize=thread
 #include "cuda_runtime.h"
 int g_mock_pageable = 1;
 #include "gsx_hostcopy.cu"
@@ -14,6 +15,12 @@ int main() {
         for (size_t i = 0; i < n; i += 4097) a[i] = (unsigned char)r();
         if (n) a[n - 1] = 0x5a;
         if (gsx::copy_h2d(dev.data(), a.data(), n, nullptr)) return 1;
+        // contract of the staged path: on return the source has been read completely -- scribbling on it now must not
+        // reach the device (the plain path of a small copy reads the source when the stream gets there: left alone)
+        const bool staged = n >= (8u << 20);
+        if (staged) a[0] ^= 0xff;
+        cudaStreamSynchronize(nullptr);         // what a kernel queued on the same stream would see
+        if (staged) a[0] ^= 0xff;
         if (memcmp(dev.data(), a.data(), n)) return 2;
         gsx::prefault_host(b.data(), n);
         if (gsx::copy_d2h(b.data(), dev.data(), n, nullptr)) return 3;

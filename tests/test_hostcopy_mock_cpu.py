@@ -1,7 +1,10 @@
 """CPU: csrc/gsx_hostcopy.cu (worker pool, chunk ring, D2H pipeline, prefault) compiled HOST-ONLY against a mock CUDA
-runtime (tests/mock_cuda: streams execute immediately) and run under ThreadSanitizer: byte-exact round trips around the
-chunk / threshold boundaries, repeated calls on the parked worker threads, several caller threads at once, no data race
-in the pool.  The real DMA ordering (events, chunk reuse) is covered on the GPU by tests/test_hostcopy_gpu.py."""
+runtime and run under ThreadSanitizer.  The mock's streams are real FIFO queues drained by background threads with a delay
+per operation (tests/mock_cuda/cuda_runtime.h), so an "async" copy happens later than its enqueue: refilling a pinned
+chunk before the event of its previous DMA, or handing a chunk to the caller before its DMA has landed, corrupts the data
+(checked once by deleting the slot-reuse wait: the harness fails at 64 MiB).  Covered: byte-exact round trips around the
+chunk / threshold boundaries, the "source fully read on return" contract, repeated calls on the parked worker threads,
+several caller threads at once, no data race.  Real hardware ordering is covered by tests/test_hostcopy_gpu.py."""
 import os
 import shutil
 import subprocess
