@@ -31,9 +31,10 @@ def _lb(q, lo, hi):
     return f32(f32(f32(d[0] * d[0]) + f32(d[1] * d[1])) + f32(d[2] * d[2]))
 
 
-def emulate(pos, k, mode="i32wrap", chunk=4, fan=4, small_bucket=6, morton_bits=2):
+def emulate(pos, k, mode="i32wrap", chunk=4, fan=4, small_bucket=6, morton_bits=2, flat_supers=0, group=32):
     """final_means float32[N] computed with the kernel's algorithm (chunk = points per chunk, fan = chunks per
-    super, small_bucket = largest bucket scanned without box tests)."""
+    super, small_bucket = largest bucket scanned without box tests, flat_supers = GSX_KNN_FLAT_SUPERS: a long bucket
+    spanning fewer supers than this tests its chunk boxes directly, `group` at a time, without the super level)."""
     pos = np.ascontiguousarray(pos, dtype=np.float32)
     n = len(pos)
     lo = pos.min(0)
@@ -111,6 +112,20 @@ def emulate(pos, k, mode="i32wrap", chunk=4, fan=4, small_bucket=6, morton_bits=
                 continue
             skip = skip_chunk if p == 13 else -1
             fc, lc = s // chunk, (e - 1) // chunk
+            def chunk_group(cands):                          # nearest chunk box first while it can still improve
+                chunks = [(c, _lb(q, *cbox[c])) for c in cands if fc <= c <= lc and c != skip]
+                chunks = [(c, l) for c, l in chunks if l < tau()]
+                while chunks:
+                    c, l = min(chunks, key=lambda t: (t[1], t[0]))
+                    if not (l < tau()):
+                        break
+                    chunks.remove((c, l))
+                    scan(max(c * chunk, s), min((c + 1) * chunk, e))
+
+            if flat_supers > 0 and lc // fan - fc // fan < flat_supers:
+                for cb in range(fc, lc + 1, group):
+                    chunk_group(range(cb, cb + group))
+                continue
             sups = [(sid, _lb(q, *sbox[sid])) for sid in range(fc // fan, lc // fan + 1)]
             # the kernel evaluates 32 supers at a time against the tau of that moment; emulate group-wise
             for g0 in range(0, len(sups), 32):
@@ -120,15 +135,7 @@ def emulate(pos, k, mode="i32wrap", chunk=4, fan=4, small_bucket=6, morton_bits=
                     if not (lb < tau()):
                         break
                     grp.remove((sid, lb))
-                    chunks = [(c, _lb(q, *cbox[c])) for c in range(sid * fan, sid * fan + fan)
-                              if fc <= c <= lc and c != skip]
-                    chunks = [(c, l) for c, l in chunks if l < tau()]
-                    while chunks:
-                        c, l = min(chunks, key=lambda t: (t[1], t[0]))
-                        if not (l < tau()):
-                            break
-                        chunks.remove((c, l))
-                        scan(max(c * chunk, s), min((c + 1) * chunk, e))
+                    chunk_group(range(sid * fan, sid * fan + fan))
         d = [np.sqrt(v) for v in lst]                        # float32 sqrt of the winners only
         vals = [v for v in d if v < f32(0.9e10)]
         ssum = f32(0)

@@ -35,3 +35,18 @@ def test_pruning_actually_prunes():
     got, st = emulate(xyz, 8, "i64", chunk=4, fan=4, small_bucket=6)
     assert st["scanned"] < 0.5 * st["visits"], st       # a large part of the reference's visits is skipped ...
     assert np.array_equal(got, oracle.sor_taichi_mean_dists(xyz, 8, "i64"))   # ... without changing a bit
+
+
+@pytest.mark.parametrize("flat,group", [(2, 3), (8, 4), (1000, 5)])
+def test_flat_walk_of_long_buckets_is_exact(flat, group):
+    """GSX_KNN_FLAT_SUPERS (shipped: 8): a long bucket spanning fewer supers than that tests its chunk boxes directly,
+    `group` at a time, in bucket order instead of nearest-super-first -- a different visiting ORDER, the same rule
+    (a chunk is skipped only while its lower bound is >= the current tau), hence the same bits."""
+    for name, pts in _clouds():
+        if name not in ("dense_blob+halo", "two_scales", "duplicates", "lattice_ties"):
+            continue
+        xyz = pts.astype(np.float32)
+        for k in (3, 16):
+            want = oracle.sor_taichi_mean_dists(xyz, k, "i32wrap")
+            got, st = emulate(xyz, k, "i32wrap", chunk=4, fan=4, small_bucket=6, flat_supers=flat, group=group)
+            assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (name, k, flat, group)
