@@ -15,11 +15,13 @@ _T2NP = {v: k for k, v in _NP2T.items()}
 
 
 def to_device(a: np.ndarray, device="cuda") -> torch.Tensor:
-    """Contiguous copy of `a` on the CURRENT CUDA device (`device` must name it)."""
+    """Contiguous copy of `a` on `device` (made current for the duration of the copy: libgsx's copy streams and
+    pinned chunks belong to the current device)."""
     a = np.ascontiguousarray(a)
     t = torch.empty(a.shape, dtype=_NP2T[a.dtype], device=device)
     if a.nbytes:
-        check(lib.gsx_copy_h2d(_ptr(t), a.ctypes.data, a.nbytes, _stream()), "gsx_copy_h2d")
+        with torch.cuda.device(t.device):
+            check(lib.gsx_copy_h2d(_ptr(t), a.ctypes.data, a.nbytes, _stream()), "gsx_copy_h2d")
     return t
 
 
@@ -28,5 +30,6 @@ def to_host(t: torch.Tensor) -> np.ndarray:
     t = t.contiguous()
     out = np.empty(tuple(t.shape), dtype=_T2NP[t.dtype])
     if out.nbytes:
-        check(lib.gsx_copy_d2h(out.ctypes.data, _ptr(t), out.nbytes, _stream()), "gsx_copy_d2h")
+        with torch.cuda.device(t.device):
+            check(lib.gsx_copy_d2h(out.ctypes.data, _ptr(t), out.nbytes, _stream()), "gsx_copy_d2h")
     return out
