@@ -1,6 +1,7 @@
 """CPU: host-side logic of the product (no GPU): cluster selection, slider maps, owner partition, bench
 reference arm.  Anything numeric is checked against the oracle / the reference's formulas."""
 import json
+import os
 import subprocess
 import sys
 from pathlib import Path
@@ -194,3 +195,56 @@ def test_bench_clock_sampler_reports_clocks_under_load(tmp_path, monkeypatch):
     import torch
     r = bench.finish_clocks(bench.ClockSampler(0), 1, 0, torch.device("cpu"), lambda: None)   # never started: no clocks
     assert r is None
+
+
+def _clock_rank(rank, world, fakedir, port, q):
+    import importlib.util
+    import time
+    import torch
+    import torch.distributed as dist
+    os.environ["PATH"] = f"{fakedir}:{os.environ['PATH']}"
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    spec = importlib.util.spec_from_file_location("_bench_mod", ROOT / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    sys.argv = ["bench.py"]
+    spec.loader.exec_module(bench)
+    c = bench.ClockSampler(0)
+    if rank == 0:
+        c.start()
+    c.window_begin()
+    time.sleep(0.02)                      # a timed region shorter than the sampler's start-up
+    c.window_end()
+    steps = [0]
+
+    def busy():                           # the extra step contains a collective, like the sharded filter
+        t = torch.ones(1)
+        dist.all_reduce(t)
+        steps[0] += 1
+        time.sleep(0.01)
+    r = bench.finish_clocks(c, world, rank, torch.device("cpu"), busy)
+    q.put((rank, steps[0], r))
+    dist.destroy_process_group()
+
+
+def test_bench_finish_clocks_is_collective_at_n_gt_1(tmp_path):
+    """N > 1: while rank 0's sampler still needs a row under load, EVERY rank must run the same number of extra
+    steps (they contain collectives) -- the decision is broadcast from rank 0; no rank may hang or diverge."""
+    import torch.multiprocessing as mp
+    fake = tmp_path / "nvidia-smi"
+    fake.write_text("#!/bin/bash\nsleep 0.2\nwhile true; do echo '0, 1965, 1965, 400.0, 0x0, Not Active, Not Active, "
+                    "Not Active, Not Active'; sleep 0.025; done\n")
+    fake.chmod(0o755)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 400)
+    procs = [ctx.Process(target=_clock_rank, args=(r, 2, str(tmp_path), port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    (r0, n0, clk0), (r1, n1, clk1) = res
+    assert n0 == n1 >= 1                                   # same number of collective busy steps on both ranks
+    assert clk1 is None and clk0 is not None and clk0["sm_mhz"] == 1965.0 and clk0["window"].startswith("extra untimed")
