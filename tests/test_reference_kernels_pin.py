@@ -159,6 +159,48 @@ def test_cuda_100k_cloud_matches_reference_source_digests(cuda, gsx_lib):
         assert _sha(np.packbits(gpu_ops.filter_sor_gpu(xyz, k=k, threshold_factor=sigma))) == str(g5[f"k{k}_mask_sha"])
 
 
+# ---- the 1 M cloud, where the kernel's int32-wrapping probe hash and the host table's int64 hash diverge
+G7 = GOLD.parent / "g7_reference_sor_1m_sample.npz"
+
+
+def _rows_to_points(xyz, rows):
+    """Original indices of points whose coordinates equal `rows` (equal coordinates => equal mean distance)."""
+    key = lambda a: np.ascontiguousarray(a).view([("", a.dtype)] * 3).ravel()   # noqa: E731
+    order = np.argsort(key(xyz), kind="stable")
+    idx = order[np.searchsorted(key(xyz)[order], key(rows))]
+    assert np.array_equal(xyz[idx], rows)
+    return idx
+
+
+@pytest.mark.skipif(not G7.exists(), reason="g7 fixture not generated")
+def test_1m_cloud_sampled_reference_kernel_vs_oracle():
+    """g7 (make_taichi_golden_1m_sample.py): the reference's kernel source over the reference's own table of the 1 M
+    cloud, for the first 30 000 rows of the hash-sorted order.  The oracle's int32-wrap reading reproduces every value;
+    the int64 reading does not (that is the regime this fixture exists for)."""
+    import oracle
+    from gsx import synth
+    g = np.load(G7)
+    xyz = synth.xyz(int(g["n"]), "mixed")
+    idx = _rows_to_points(xyz, g["rows"])
+    md = oracle.sor_taichi_mean_dists(xyz, int(g["k"]), "i32wrap")
+    assert np.array_equal(md[idx].view(np.uint32), g["means"].view(np.uint32))
+    md64 = oracle.sor_taichi_mean_dists(xyz, int(g["k"]), "i64")
+    differ = int((md64[idx].view(np.uint32) != g["means"].view(np.uint32)).sum())
+    assert differ == int(g["differ_from_i64"]) and differ > 1000
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not G7.exists(), reason="g7 fixture not generated")
+def test_cuda_1m_cloud_matches_sampled_reference_kernel(cuda, gsx_lib):
+    import torch
+    from gsx import sor, synth
+    g = np.load(G7)
+    xyz = synth.xyz(int(g["n"]), "mixed")
+    idx = _rows_to_points(xyz, g["rows"])
+    _, md = sor.sor_filter(torch.from_numpy(xyz).to(cuda), int(g["k"]), 2.0, hash_mode="i32wrap", return_means=True)
+    assert np.array_equal(md.cpu().numpy()[idx].view(np.uint32), g["means"].view(np.uint32))
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 def test_cuda_sor_matches_reference_kernel_outputs(cuda, gsx_lib):
