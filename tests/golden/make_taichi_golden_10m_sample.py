@@ -1,0 +1,64 @@
+"""One-off (~35 min of CPU): as make_taichi_golden_1m_sample.py, on BASELINE configs[1] itself -- the 10 M `mixed` cloud of
+the headline metric (SOR k=16): the reference's own `filter_sor_gpu` host driver builds its table over all 10 M points and
+its `sor_compute_mean_dists` kernel source runs (serial `taichi` stand-in, ~0.1 s per query at 48 746 candidate visits per
+point) for the first M = 8 000 rows of the hash-sorted order; the clipped launch is the only intervention.  Asserted
+bit-identical to the oracle (int32-wrap reading); writes tests/golden/g8_reference_sor_10m_sample.npz.
+
+    python tests/golden/make_taichi_golden_10m_sample.py
+"""
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+ROOT = HERE.parent.parent
+sys.path.insert(0, str(HERE))
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "3dgsconverter_b200"))
+
+import oracle  # noqa: E402
+import ti_serial  # noqa: E402
+from gsx import synth  # noqa: E402
+
+M = 8_000
+K = 16
+
+
+def main():
+    ref = ti_serial.import_reference_gpu_ops()
+    real_kernel = ref.sor_compute_mean_dists
+    seen = {}
+
+    def clipped(pos, cell_start, cell_count, mean_dists, bx, by, bz, cell, hash_size, N, Kk):
+        seen.update(pos=pos, mean_dists=mean_dists, hash_size=hash_size, N=N, K=Kk, cell=cell)
+        real_kernel(pos, cell_start, cell_count, mean_dists, bx, by, bz, cell, hash_size, min(N, M), Kk)
+
+    ref.sor_compute_mean_dists = clipped
+    xyz = synth.xyz(10_000_000, "mixed")
+    t0 = time.time()
+    ref.filter_sor_gpu(xyz.copy(), k=K, threshold_factor=2.0)     # (its mask is meaningless: most rows were not processed)
+    print(f"reference host driver + clipped kernel: {time.time() - t0:.0f} s", flush=True)
+    assert seen["hash_size"] == 10_000_000 and seen["N"] == 10_000_000 and seen["K"] == K
+    rows = np.ascontiguousarray(seen["pos"][:M])
+    got = np.ascontiguousarray(seen["mean_dists"][:M])
+    want32 = oracle.sor_taichi_mean_dists(xyz, K, "i32wrap")
+    want64 = None       # (the int64 reading at this size: 10 more CPU-minutes, not needed for the pin)
+    # match the processed rows to original points by coordinates (points with equal coordinates have equal means)
+    key = lambda a: np.ascontiguousarray(a).view([("", a.dtype)] * 3).ravel()   # noqa: E731
+    order = np.argsort(key(xyz), kind="stable")
+    pos_in_sorted = np.searchsorted(key(xyz)[order], key(rows))
+    idx = order[pos_in_sorted]
+    assert np.array_equal(xyz[idx], rows)
+    assert np.array_equal(got.view(np.uint32), want32[idx].view(np.uint32)), "oracle (i32wrap) != reference kernel"
+    differ = -1
+    print(f"{M} queries of the 10 M cloud: reference kernel == oracle(i32wrap) bit for bit; "
+          f"{int((got == 0).sum())} have no candidate at all (mean 0.0)")
+    np.savez_compressed(HERE / "g8_reference_sor_10m_sample.npz", rows=rows, means=got, k=K, n=10_000_000, m=M,
+                        differ_from_i64=differ)
+    print("wrote g8_reference_sor_10m_sample.npz")
+
+
+if __name__ == "__main__":
+    main()
