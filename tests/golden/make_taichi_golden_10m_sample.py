@@ -1,7 +1,7 @@
 """One-off (~35 min of CPU): as make_taichi_golden_1m_sample.py, on BASELINE configs[1] itself -- the 10 M `mixed` cloud of
 the headline metric (SOR k=16): the reference's own `filter_sor_gpu` host driver builds its table over all 10 M points and
 its `sor_compute_mean_dists` kernel source runs (serial `taichi` stand-in, ~0.1 s per query at 48 746 candidate visits per
-point) for the first M = 8 000 rows of the hash-sorted order; the clipped launch is the only intervention.  Asserted
+point) for the first M = 50 000 rows of the hash-sorted order; the clipped launch is the only intervention.  Asserted
 bit-identical to the oracle (int32-wrap reading); writes tests/golden/g8_reference_sor_10m_sample.npz.
 
     python tests/golden/make_taichi_golden_10m_sample.py
@@ -22,7 +22,7 @@ import oracle  # noqa: E402
 import ti_serial  # noqa: E402
 from gsx import synth  # noqa: E402
 
-M = 8_000
+M = 50_000
 K = 16
 
 
