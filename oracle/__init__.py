@@ -13,7 +13,8 @@ cannot be installed here, so nothing below was ever compared with a Taichi RUN. 
     (11 SOR runs on 8 clouds <= 3000 points, 4 K-Means problems) and g5_reference_sor_100k.npz (BASELINE
     configs[0]: the 100 k cloud, k=27 / --sor_intensity 5 and k=16) and g6_reference_kmeans_c3shape.npz (one
     20 011 x 45, K=256 Lloyd problem -- the C3 / tensor-core shape), tests/test_reference_kernels_pin.py.
-    g7_reference_sor_1m_sample.npz: 30 000 queries of the 1 M cloud (the regime where int32-wrap != int64).
+    g7_reference_sor_1m_sample.npz: 30 000 queries of the 1 M cloud (the regime where int32-wrap != int64);
+    g8_reference_sor_10m_sample.npz: 50 000 queries of the 10 M cloud of BASELINE configs[1].
     Beyond these fixtures the parity rests on this restatement plus the survey's anchor counts ("parity unpinned").
   * density / alpha / bbox / cKDTree SOR arithmetic: to the imported reference (tests/golden/make_goldens.py);
   * NumPy-visible arithmetic (pairwise mean/std, promotion rules): to NumPy itself (tests/test_oracle_pins.py).

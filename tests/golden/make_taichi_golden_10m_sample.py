@@ -1,8 +1,9 @@
-"""One-off (~35 min of CPU): as make_taichi_golden_1m_sample.py, on BASELINE configs[1] itself -- the 10 M `mixed` cloud of
+"""One-off (~50 min of CPU): as make_taichi_golden_1m_sample.py, on BASELINE configs[1] itself -- the 10 M `mixed` cloud of
 the headline metric (SOR k=16): the reference's own `filter_sor_gpu` host driver builds its table over all 10 M points and
-its `sor_compute_mean_dists` kernel source runs (serial `taichi` stand-in, ~0.1 s per query at 48 746 candidate visits per
-point) for the first M = 50 000 rows of the hash-sorted order; the clipped launch is the only intervention.  Asserted
-bit-identical to the oracle (int32-wrap reading); writes tests/golden/g8_reference_sor_10m_sample.npz.
+its `sor_compute_mean_dists` kernel source runs (serial `taichi` stand-in, ~2 us per candidate visit) for the first
+M = 50 000 rows of the hash-sorted order -- 1.35e9 candidate visits, up to 280 000 per query: the sample crosses one of
+the giant cluster buckets; the clipped launch is the only intervention (the first 200 000 rows would take ~11 h).
+Asserted bit-identical to the oracle (int32-wrap reading); writes tests/golden/g8_reference_sor_10m_sample.npz.
 
     python tests/golden/make_taichi_golden_10m_sample.py
 """
